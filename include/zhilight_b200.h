@@ -1,0 +1,224 @@
+/*
+ * zhilight_b200 -- C-ABI of the B200-native (sm_100a) quantized-decode hot path of ZhiLight.
+ *
+ * Every entry point replaces one reference operator (cited as file:line under /root/reference).
+ * Conventions:
+ *   - plain pointers + sizes, no C++/torch types; all data pointers are DEVICE pointers unless
+ *     the name ends in _host;
+ *   - stream-ordered on `stream`, no allocation, no host sync inside (except zl_llama_* which
+ *     owns its buffers);
+ *   - returns ZL_OK (0) or a negative error code; zl_last_error() gives the message of the last
+ *     failure on the calling thread.  The C++ mirror (zhilight_b200/host) turns codes into the
+ *     reference's BMEngineException behaviour;
+ *   - re-entrant per device; no global mutable state besides per-device symmetric buffers
+ *     created by zl_comm_*.
+ *
+ * dtype codes follow bmengine core::DataType ordering where they overlap
+ * (3rd/bmengine/bmengine/include/bmengine/core/dtype.h).
+ */
+#ifndef ZHILIGHT_B200_H_
+#define ZHILIGHT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* zl_stream_t; /* == cudaStream_t */
+
+enum {
+    ZL_OK = 0,
+    ZL_ERR_INVALID_ARG = -1,
+    ZL_ERR_UNSUPPORTED = -2,
+    ZL_ERR_CUDA = -3,
+    ZL_ERR_STATE = -4
+};
+
+enum { ZL_F16 = 0, ZL_BF16 = 1, ZL_F32 = 2 };
+
+/* epilogues of zl_w4a16_gemm */
+enum {
+    ZL_EPI_NONE = 0,     /* y = acc (+bias)                                                     */
+    ZL_EPI_SWIGLU = 1,   /* packed rows interleave gate/up; y[:, n] = silu(T(gate)) * T(up)      */
+    ZL_EPI_RESIDUAL = 2  /* y = T(T(acc (+bias)) + residual)   (block_kernel.cu:7-17)           */
+};
+
+const char* zl_last_error(void);
+int zl_version(void);
+/* number of kernel launches issued by this library on the calling thread since the last reset */
+long long zl_launch_count(int reset);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Load-time integer layout transforms (bit-exact with the reference)
+ * ------------------------------------------------------------------------------------------ */
+/* nn::gptq::gptq_shuffle  (src/nn/quant/gptq/q_gemm.cu:778-872, qdq_4.cuh:16-35).
+ * qweight (K/8, N) int32 in place.  q_perm (K) int32 or NULL; scratch (K/8*N words) required iff q_perm. */
+int zl_gptq_shuffle(uint32_t* qweight, const int32_t* q_perm, uint32_t* scratch, int K, int N,
+                    zl_stream_t stream);
+/* nn::gptq::increase_zero (src/nn/quant/gptq/utils.cu:61-88): each nibble (z+1)&15, in place. */
+int zl_gptq_increase_zero(uint32_t* qzeros, size_t n_words, zl_stream_t stream);
+/* nn::gptq::subtract8 (utils.cu:91-118). */
+int zl_gptq_subtract8(uint32_t* words, size_t n_words, zl_stream_t stream);
+/* nn::gptq::q4_to_q8 (utils.cu:177-214): (R, C/8) int32 -> (R, C) uint8. */
+int zl_q4_to_q8(const uint32_t* in, uint8_t* out, size_t n_words, zl_stream_t stream);
+/* nn::gptq::un_shuffle (utils.cu:25-58): AWQ zero de-interleave in place, (rows, cols) words. */
+int zl_awq_un_shuffle(uint32_t* qzeros, int rows, int cols, zl_stream_t stream);
+/* nn::gptq::shuffle_awq (utils.cu:121-174): (K, N/8) -> (K/8, N). */
+int zl_awq_shuffle(const uint32_t* in, uint32_t* out, int K, int N, int use_exllama, zl_stream_t stream);
+/* functions::Transpose for 2-D tensors of 1/2/4-byte elements: (rows, cols) -> (cols, rows). */
+int zl_transpose_2d(const void* in, void* out, int rows, int cols, int elem_bytes, zl_stream_t stream);
+/* nn::gptq::dequant_k_major out_type 0 (q_gemm_k_major.cu:843-905): W16[n,k] = half(q-z)*half(s). */
+int zl_gptq_dequant_k_major(const uint32_t* qweight_km, const uint8_t* qzeros_km, const void* scales_km,
+                            void* out_f16, int N, int K, int group_size, zl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * ZLW4: the B200 tile-packed W4 layout consumed by zl_w4a16_gemm.
+ * Built once at load from the reference k-major tensors
+ * (Int4GPTQ::preprocess_weight, src/nn/linear/linear.cpp:1139-1160).
+ * ------------------------------------------------------------------------------------------ */
+size_t zl_w4_packed_bytes(int N, int K, int group_size);
+/* qweight_km (N_src, K/8) u32 shuffled, qzeros_km (N_src, K/g) u8 (NULL or sym!=0 -> zero 8),
+ * scales_km (N_src, K/g) f16.  row_map (N) int32 or NULL: packed row p takes source row row_map[p]. */
+int zl_w4_pack(const uint32_t* qweight_km, const uint8_t* qzeros_km, const void* scales_km,
+               const int32_t* row_map, void* packed, int N, int K, int group_size, int sym,
+               zl_stream_t stream);
+/* inverse (tests): recover k-major nibbles/zeros/scales from the packed form. */
+int zl_w4_unpack(const void* packed, uint32_t* qweight_km, uint8_t* qzeros_km, void* scales_km, int N, int K,
+                 int group_size, zl_stream_t stream);
+
+/* nn::gptq::gptq_gemm_k_major / KERNEL_gemm_warp_reduce / gemm_fuse_gate_in
+ * (src/nn/quant/gptq/q_gemm_k_major.cu:957-1116, 176-237, 529-578):
+ * y[m,n] = sum_k x[m,k] * (q[n,k]-z[n,k/g]) * s[n,k/g] (+bias[n]), fp16 in/out, fp32 accumulate.
+ * x (M, K) f16 row stride ldx; y (M, N_out) f16 where N_out = N (NONE/RESIDUAL) or N/2 (SWIGLU).
+ * Any M >= 1 (weights are re-streamed per 32-token chunk).  pdl != 0 -> programmatic dependent launch. */
+int zl_w4a16_gemm(const void* x, int ldx, const void* packed, const void* bias, const void* residual,
+                  void* y, int M, int N, int K, int group_size, int epilogue, int pdl, zl_stream_t stream);
+
+/* functions::Gemm / NormalLinear for skinny M (lm_head, bf16 models; src/nn/linear/linear.cpp:150-430,
+ * src/nn/embedding/embedding.cu:353-392): y(M,N) = x(M,K) @ W(N,K)^T (+bias), dtype f16/bf16,
+ * out_dtype f16/bf16/f32. */
+int zl_dense_gemm_skinny(const void* x, int ldx, const void* w, const void* bias, void* y, int M, int N, int K,
+                         int dtype, int out_dtype, int pdl, zl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Norm / residual / activation
+ * ------------------------------------------------------------------------------------------ */
+/* nn::LayerNorm::forward, rms (src/nn/layernorm/layernorm.cu:9-42): y = T(x*rsqrt(mean(x^2)+eps)*w/scale). */
+int zl_rmsnorm(const void* x, const void* weight, void* y, int T, int D, float eps, float scale, int dtype,
+               int pdl, zl_stream_t stream);
+/* Residual + RMSNorm.  mode 0: block.cpp:124-131 order -- out_sum = T(a+b) (block_kernel.cu:7-17),
+ * y = rmsnorm(out_sum);  mode 1: LayerNorm::fuse_add (layernorm.cu:28-41) -- y normalises the unrounded sum.
+ * b may be NULL (then out_sum = a).  out_sum may alias a. */
+int zl_add_rmsnorm(const void* a, const void* b, const void* weight, void* out_sum, void* y, int T, int D,
+                   float eps, float scale, int mode, int dtype, int pdl, zl_stream_t stream);
+/* nn::element_add_scale (src/nn/block/block_kernel.cu:7-17), scale_residual=false:
+ * c = T(a + T(b*scale))  computed in T. */
+int zl_element_add_scale(const void* a, const void* b, void* c, size_t n, float scale, int dtype,
+                         zl_stream_t stream);
+/* nn::gate_mul_inplace (src/nn/linear/activation_kernel.cu:55-106): out = T(act(float(gate))*float(up));
+ * act 0 = silu, 1 = gelu.  gate/up (T, F) with row strides. */
+int zl_gate_mul(const void* gate, int ld_gate, const void* up, int ld_up, void* out, int ld_out, int T, int F,
+                int act, int dtype, zl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * RoPE + KV append
+ * ------------------------------------------------------------------------------------------ */
+/* RopePreparer (src/nn/position/rope_preparer.cu:49-161): cos/sin fp32 (T, d).
+ * llama3_factor <= 0 -> plain rope. */
+int zl_rope_cos_sin(const int32_t* pos, float* cos_out, float* sin_out, int T, int dim_head, float theta,
+                    float llama3_factor, float low_freq_factor, float high_freq_factor, float old_context_len,
+                    int neox, zl_stream_t stream);
+/* nn::rope_qk_cache (src/nn/position/rotary_embedding_fuse_cache.cu:23-125): split fused qkv and rotate q,k. */
+int zl_rope_qk_cache(const float* cos, const float* sin, const void* qkv, void* q, void* k, void* v, int T,
+                     int num_heads, int num_kv_heads, int dim_head, int neox, int dtype, zl_stream_t stream);
+/* nn copy_to_rag_buffer2 (src/kvcache/ragged_buffer_kernel.cu:194-300). */
+int zl_copy_to_rag_buffer2(const int32_t* placement, const int32_t* buf_lens, const void* k_src,
+                           const void* v_src, void* const* k_addrs, void* const* v_addrs, int B, int len_q,
+                           int num_kv_heads, int dim_head, int bshd, int dtype, zl_stream_t stream);
+/* Fused: split qkv (+bias already applied) + RoPE(q,k) + append K/V rows at placement into the per-task
+ * buffers + write rotated q.  Replaces rope_qk_cache + copy_to_rag_buffer2 (attention.cpp:865-898, 636-676).
+ * token_batch (T) int32: task index of each token; placement (T) int32 (<0: skip append). */
+int zl_qkv_rope_append(const float* cos, const float* sin, const void* qkv, void* q_out,
+                       const int32_t* token_batch, const int32_t* placement, void* const* k_addrs,
+                       void* const* v_addrs, int T, int num_heads, int num_kv_heads, int dim_head, int neox,
+                       int bshd, const int32_t* buf_lens, int dtype, int pdl, zl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Decode attention over per-task ragged KV buffers
+ * nn::multi_query_attention_rag_buffer (src/nn/attention/attention_kernel.cu:1252-1457)
+ * ------------------------------------------------------------------------------------------ */
+size_t zl_decode_attention_workspace_bytes(int B, int len_q, int num_heads, int dim_head, int max_len_buf);
+/* q (B, len_q, H_q, d); buf_lens (B); k_addrs/v_addrs (B) device arrays of device pointers;
+ * mask int8 ragged concat of (len_q, len_buf_b); out (B, len_q, H_q, d).  bshd: (len_buf, H_kv, d) else
+ * (H_kv, len_buf, d). */
+int zl_decode_attention(const void* q, const int32_t* buf_lens, void* const* k_addrs, void* const* v_addrs,
+                        const int8_t* mask, float scale, int max_len_buf, void* out, int B, int len_q,
+                        int num_heads, int num_kv_heads, int dim_head, int bshd, void* workspace,
+                        size_t workspace_bytes, int dtype, int pdl, zl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Decode-step helpers around the layers
+ * ------------------------------------------------------------------------------------------ */
+/* nn::Embedding lookup (src/nn/embedding/embedding.cu:20-60): out[t,:] = table[ids[t],:]. */
+int zl_embedding(const int32_t* ids, const void* table, void* out, int T, int D, int vocab, int dtype, int pdl,
+                 zl_stream_t stream);
+/* greedy pick (generator/batch_generator.cpp:1762-1884 with beam 1): argmax over fp32 logits (T, V). */
+size_t zl_argmax_workspace_bytes(int T);
+int zl_argmax(const float* logits, int32_t* out, int T, int V, void* workspace, size_t workspace_bytes, int pdl,
+              zl_stream_t stream);
+/* synthetic-checkpoint generators (bench / tests): counter-based hash RNG, reproducible per seed. */
+int zl_fill_random_u32(uint32_t* p, size_t n, uint64_t seed, zl_stream_t stream);
+int zl_fill_const_u32(uint32_t* p, size_t n, uint32_t value, zl_stream_t stream);
+int zl_fill_uniform(void* p, size_t n, float lo, float hi, uint64_t seed, int dtype, zl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Decode driver: the model::LLaMA::encode + get_logits + greedy pick stand-in
+ * (src/model/llama.cpp:75-165, src/nn/block/block.cpp:86-143, src/nn/attention/attention.cpp:846-964,
+ *  src/nn/feedforward/feedforward.cpp:113-137) for len_q = 1 dynamic-batch steps.  The reference keeps
+ * its scheduler (src/generator) above this; here the caller supplies (token, position) per task.
+ * One CUDA graph per batch size, all kernels chained with programmatic dependent launch.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct zl_llama zl_llama_t;
+typedef struct zl_llama_config {
+    int num_layers, dim_model, num_heads, num_kv_heads, dim_head, dim_ff, vocab_size;
+    float eps, rope_theta;
+    float rope_llama3_factor; /* <= 0: plain rope */
+    float rope_low_freq_factor, rope_high_freq_factor, rope_orig_ctx;
+    int quant_type; /* model_config.hpp:132-144 QuantType: 0 none, 5 GPTQ, 6 AWQ */
+    int group_size, sym;
+    int dtype; /* ZL_F16 / ZL_BF16 (W4 paths are fp16-only like the reference, q_gemm_k_major.cu:989) */
+    int max_batch, max_seq;
+    int tp_rank, tp_size;
+    int use_pdl, use_graph;
+} zl_llama_config_t;
+
+int zl_llama_create(const zl_llama_config_t* cfg, zl_llama_t** out);
+void zl_llama_destroy(zl_llama_t* m);
+/* Stage one checkpoint tensor (HOST pointer, row-major (rows, cols)); names as produced by
+ * zhilight/loader.py:250-358 without the "llama." prefix, e.g. "layers.0.attn.project_q.qweight". */
+int zl_llama_load_tensor(zl_llama_t* m, const char* name, const void* data_host, int rows, int cols,
+                         int elem_bytes);
+/* Fill every tensor of the configured architecture with reproducible random data ON DEVICE
+ * (HF-GPTQ layout for quantized linears) and run the load pipeline layer by layer. */
+int zl_llama_init_synthetic(zl_llama_t* m, uint64_t seed);
+/* Run the load pipeline (Int4GPTQ::preprocess_weight + fusion + ZLW4 pack) on the staged tensors. */
+int zl_llama_finalize(zl_llama_t* m);
+/* One decode step for B tasks.  tokens_host/positions_host (B) int32; task b owns KV slot b.
+ * next_tokens_host (B) int32 greedy picks; logits_host NULL or (B, vocab) fp32.  Synchronous. */
+int zl_llama_decode(zl_llama_t* m, const int32_t* tokens_host, const int32_t* positions_host, int B,
+                    int32_t* next_tokens_host, float* logits_host);
+/* Device-resident variant: stage tokens/positions once, then each call replays the step, feeds the picked
+ * tokens back and advances positions on the device; no host sync. */
+int zl_llama_set_state(zl_llama_t* m, const int32_t* tokens_host, const int32_t* positions_host, int B);
+int zl_llama_step_device(zl_llama_t* m, int B);
+int zl_llama_sync(zl_llama_t* m);
+zl_stream_t zl_llama_stream(zl_llama_t* m);
+/* bytes the step must read from HBM per rank (weights + lm_head + norms), kernel launches per step. */
+int zl_llama_stats(zl_llama_t* m, int B, double* weight_bytes, int* kernels_per_step);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZHILIGHT_B200_H_ */

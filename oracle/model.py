@@ -1,0 +1,140 @@
+"""CPU oracle: a whole Llama decode step (numpy), assembled from oracle.gptq / oracle.ops.
+
+TEST INFRASTRUCTURE -- see oracle/__init__.py.  Follows the reference's single-stream decode order
+(src/nn/block/block.cpp:86-143, src/nn/attention/attention.cpp:846-964,
+src/nn/feedforward/feedforward.cpp:113-137, src/model/llama.cpp:75-165): every operator output is
+rounded to the activation dtype T exactly where the reference materialises a T tensor.
+"""
+import numpy as np
+
+from . import gptq, ops
+
+F32 = np.float32
+
+
+class OracleLlama:
+    def __init__(self, cfg, state_dict, quant_type=0, group_size=128, sym=False, dtype="f16"):
+        """cfg: dict with num_layers, dim_model, num_heads, num_kv_heads, dim_head, dim_ff, vocab_size, eps,
+        rope_theta, rope_llama3.  state_dict: HF/ZhiLight-named numpy tensors."""
+        self.c = dict(cfg)
+        self.dtype = dtype
+        self.sd = state_dict
+        self.quant_type = quant_type
+        self.group_size = group_size
+        self.sym = sym
+        self.w = {}
+        self.kv = {}          # task -> list over layers of (k (cap,Hkv,d), v)
+
+    def _weight(self, prefix):
+        """(N, K) fp32 dequantized weight of one Linear."""
+        if prefix in self.w:
+            return self.w[prefix]
+        sd = self.sd
+        if self.quant_type == 5:
+            qw, qz, sc, _ = gptq.to_k_major(sd[prefix + ".qweight"], sd[prefix + ".qzeros"], sd[prefix + ".scales"],
+                                            None, self.group_size)
+            w = gptq.dequant_k_major_f32(qw, qz, sc, self.sym)
+        elif self.quant_type == 6:
+            qw, qz, sc, _ = gptq.to_k_major(sd[prefix + ".qweight"], sd[prefix + ".qzeros"], sd[prefix + ".scales"],
+                                            None, self.group_size, is_awq=True)
+            w = gptq.dequant_k_major_f32(qw, qz, sc, False)
+        else:
+            w = ops._t(np.asarray(sd[prefix + ".weight"], dtype=F32), self.dtype)
+        self.w[prefix] = w
+        return w
+
+    def _linear(self, x, prefix):
+        y = np.asarray(x, F32) @ self._weight(prefix).T
+        b = self.sd.get(prefix + ".bias")
+        if b is not None:
+            y = y + np.asarray(b, F32)[None, :]
+        return ops._t(y, self.dtype)
+
+    def decode(self, tokens, positions, tasks=None):
+        """One step for B tasks; returns logits (B, V) fp32.  Task b appends its K/V at positions[b]."""
+        c, T = self.c, self.dtype
+        b = len(tokens)
+        tasks = list(range(b)) if tasks is None else tasks
+        d, hq, hkv = c["dim_head"], c["num_heads"], c["num_kv_heads"]
+        emb = ops._t(np.asarray(self.sd["token_embedding.weight"], F32), T)
+        h = emb[np.asarray(tokens)]
+        cos, sin = ops.rope_cos_sin(np.asarray(positions), d, c["rope_theta"], c.get("rope_llama3"))
+        scale = F32(1.0 / np.sqrt(d))
+        for l in range(c["num_layers"]):
+            p = "layers.%d." % l
+            xn = ops.rmsnorm(h, self.sd[p + "ln_attn.weight"], c["eps"], 1.0, T)
+            q = self._linear(xn, p + "attn.project_q")
+            k = self._linear(xn, p + "attn.project_k")
+            v = self._linear(xn, p + "attn.project_v")
+            qkv = np.concatenate([q, k, v], axis=1)
+            q, k, v = ops.split_qkv_rope(qkv, cos, sin, hq, hkv, d, True, T)
+            ao = np.zeros((b, hq * d), F32)
+            for i, task in enumerate(tasks):
+                kvs = self.kv.setdefault(task, [None] * c["num_layers"])
+                if kvs[l] is None:
+                    kvs[l] = (np.zeros((0, hkv, d), F32), np.zeros((0, hkv, d), F32))
+                kb, vb = kvs[l]
+                pos = int(positions[i])
+                if kb.shape[0] <= pos:
+                    pad = np.zeros((pos + 1 - kb.shape[0], hkv, d), F32)
+                    kb, vb = np.concatenate([kb, pad]), np.concatenate([vb, pad])
+                kb[pos] = k[i].reshape(hkv, d)
+                vb[pos] = v[i].reshape(hkv, d)
+                kvs[l] = (kb, vb)
+                lb = pos + 1
+                o = ops.decode_attention(q[i].reshape(1, 1, hq, d), [kb], [vb], [lb],
+                                         [np.ones((1, lb), np.int8)], scale, hq // hkv, T)
+                ao[i] = o.reshape(-1)
+            o = self._linear(ao, p + "attn.attn_out")
+            h = ops.residual_add(h, o, T)
+            xn = ops.rmsnorm(h, self.sd[p + "ln_ff.weight"], c["eps"], 1.0, T)
+            g = self._linear(xn, p + "ff.w_in")
+            u = self._linear(xn, p + "ff.w_gated")
+            act = ops.silu_mul(g, u, T)
+            dn = self._linear(act, p + "ff.w_out")
+            h = ops.residual_add(h, dn, T)
+        xn = ops.rmsnorm(h, self.sd["output_layernorm.weight"], c["eps"], 1.0, T)
+        lm = self.sd.get("lm_head.weight", self.sd["token_embedding.weight"])
+        return np.asarray(xn, F32) @ ops._t(np.asarray(lm, F32), T).T
+
+
+def make_state_dict(cfg, quant_type=0, group_size=128, sym=False, seed=0, tied=False):
+    """Random checkpoint with ZhiLight names (zhilight/loader.py:250-358)."""
+    rng = np.random.default_rng(seed)
+    c = cfg
+    d_model, d = c["dim_model"], c["dim_head"]
+    sd = {}
+
+    def dense(n, k):
+        return (rng.standard_normal((n, k)) * 0.05).astype(np.float16)
+
+    def linear(prefix, k, n, s):
+        if quant_type == 5:
+            qw, qz, sc, gi = gptq.make_gptq_checkpoint(k, n, group_size, sym, s)
+            sd[prefix + ".qweight"], sd[prefix + ".qzeros"], sd[prefix + ".scales"] = qw, qz, sc
+        elif quant_type == 6:
+            r = np.random.default_rng(s)
+            sd[prefix + ".qweight"] = r.integers(0, 2 ** 32, size=(k, n // 8), dtype=np.uint64).astype(np.uint32).view(np.int32)
+            sd[prefix + ".qzeros"] = r.integers(0, 2 ** 32, size=(k // group_size, n // 8), dtype=np.uint64).astype(np.uint32).view(np.int32)
+            sd[prefix + ".scales"] = (0.005 + 0.015 * r.random((k // group_size, n))).astype(np.float16)
+        else:
+            sd[prefix + ".weight"] = dense(n, k)
+
+    s = seed * 1000
+    for l in range(c["num_layers"]):
+        p = "layers.%d." % l
+        sd[p + "ln_attn.weight"] = (1.0 + 0.1 * rng.standard_normal(d_model)).astype(np.float16)
+        sd[p + "ln_ff.weight"] = (1.0 + 0.1 * rng.standard_normal(d_model)).astype(np.float16)
+        linear(p + "attn.project_q", d_model, c["num_heads"] * d, s + 1)
+        linear(p + "attn.project_k", d_model, c["num_kv_heads"] * d, s + 2)
+        linear(p + "attn.project_v", d_model, c["num_kv_heads"] * d, s + 3)
+        linear(p + "attn.attn_out", c["num_heads"] * d, d_model, s + 4)
+        linear(p + "ff.w_in", d_model, c["dim_ff"], s + 5)
+        linear(p + "ff.w_gated", d_model, c["dim_ff"], s + 6)
+        linear(p + "ff.w_out", c["dim_ff"], d_model, s + 7)
+        s += 10
+    sd["token_embedding.weight"] = dense(c["vocab_size"], d_model)
+    sd["output_layernorm.weight"] = (1.0 + 0.1 * rng.standard_normal(d_model)).astype(np.float16)
+    if not tied:
+        sd["lm_head.weight"] = dense(c["vocab_size"], d_model)
+    return sd

@@ -1,0 +1,161 @@
+// Skinny dense GEMM y(M,N) = x(M,K) @ W(N,K)^T for M <= 32 per pass (lm_head, bf16/fp16 Linear at decode).
+//
+// Replaces the cuBLASLt GEMV the reference uses for unquantized Linear / lm_head at decode
+// (src/nn/linear/linear.cpp:150-430 NormalLinear, src/nn/embedding/embedding.cu:353-392).
+// HBM-bound: W is streamed once, straight from global memory into mma.sync A fragments
+// (16-byte non-allocating loads, 4 k-steps in flight per warp); a k-permutation shared by the A and
+// B fragments makes every load a contiguous 16 bytes.
+#include "common.cuh"
+
+namespace zl {
+
+constexpr int kDenseWarps = 4;
+constexpr int kDenseUnroll = 4;   // k-steps (32 k each) in flight
+
+template <typename T>
+__device__ __forceinline__ void mma_t(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
+template <>
+__device__ __forceinline__ void mma_t<__half>(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    mma_16816_f16(d, a, b0, b1, d);
+}
+template <>
+__device__ __forceinline__ void mma_t<__nv_bfloat16>(float (&d)[4], const uint32_t (&a)[4], uint32_t b0,
+                                                     uint32_t b1) {
+    mma_16816_bf16(d, a, b0, b1, d);
+}
+
+template <typename T, typename TO, int NT>
+__global__ void __launch_bounds__(kDenseWarps * 32)
+k_dense_skinny(const T* __restrict__ x, int ldx, const T* __restrict__ w, const T* __restrict__ bias,
+               TO* __restrict__ y, int mc, int N, int K) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int tile = blockIdx.x * kDenseWarps + warp;
+    const int row0 = tile * 16;
+    pdl_trigger();
+    if (row0 >= N) {
+        pdl_wait();
+        return;
+    }
+    const int ra = min(row0 + g, N - 1), rb = min(row0 + g + 8, N - 1);
+    const T* wa = w + (size_t)ra * K + t * 8;
+    const T* wb = w + (size_t)rb * K + t * 8;
+    const int steps = K / 32;
+
+    uint4 na[kDenseUnroll], nb[kDenseUnroll];
+#pragma unroll
+    for (int u = 0; u < kDenseUnroll; ++u) {
+        if (u < steps) {
+            na[u] = ld_nc_na_u4(wa + u * 32);
+            nb[u] = ld_nc_na_u4(wb + u * 32);
+        }
+    }
+    pdl_wait();
+
+    float acc[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[nt][c] = 0.f;
+
+    for (int s0 = 0; s0 < steps; s0 += kDenseUnroll) {
+        uint4 ca[kDenseUnroll], cb[kDenseUnroll];
+#pragma unroll
+        for (int u = 0; u < kDenseUnroll; ++u) {
+            ca[u] = na[u];
+            cb[u] = nb[u];
+        }
+        uint4 xb[kDenseUnroll][NT];
+#pragma unroll
+        for (int u = 0; u < kDenseUnroll; ++u)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const int tok = nt * 8 + g;
+                xb[u][nt] = (tok < mc && s0 + u < steps)
+                                ? ld_cg_u4(x + (size_t)tok * ldx + (size_t)(s0 + u) * 32 + t * 8)
+                                : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+        for (int u = 0; u < kDenseUnroll; ++u) {
+            const int sn = s0 + kDenseUnroll + u;
+            if (sn < steps) {
+                na[u] = ld_nc_na_u4(wa + (size_t)sn * 32);
+                nb[u] = ld_nc_na_u4(wb + (size_t)sn * 32);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kDenseUnroll; ++u) {
+            if (s0 + u < steps) {
+                const uint32_t a0[4] = {ca[u].x, cb[u].x, ca[u].y, cb[u].y};
+                const uint32_t a1[4] = {ca[u].z, cb[u].z, ca[u].w, cb[u].w};
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    mma_t<T>(acc[nt], a0, xb[u][nt].x, xb[u][nt].y);
+                    mma_t<T>(acc[nt], a1, xb[u][nt].z, xb[u][nt].w);
+                }
+            }
+        }
+    }
+
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int tok = nt * 8 + 2 * t + (c & 1);
+            const int row = row0 + g + ((c >> 1) ? 8 : 0);
+            if (tok < mc && row < N) {
+                float v = acc[nt][c];
+                if (bias) v += to_f32<T>(bias[row]);
+                y[(size_t)tok * N + row] = from_f32<TO>(v);
+            }
+        }
+    }
+}
+
+template <typename T, typename TO>
+static cudaError_t launch_dense(const T* x, int ldx, const T* w, const T* bias, TO* y, int mc, int N, int K,
+                                bool pdl, cudaStream_t stream) {
+    const int tiles = cdiv(N, 16);
+    dim3 grid(cdiv(tiles, kDenseWarps)), block(kDenseWarps * 32);
+    if (mc <= 8) return launch(k_dense_skinny<T, TO, 1>, grid, block, 0, stream, pdl, x, ldx, w, bias, y, mc, N, K);
+    if (mc <= 16) return launch(k_dense_skinny<T, TO, 2>, grid, block, 0, stream, pdl, x, ldx, w, bias, y, mc, N, K);
+    return launch(k_dense_skinny<T, TO, 4>, grid, block, 0, stream, pdl, x, ldx, w, bias, y, mc, N, K);
+}
+
+template <typename T>
+static cudaError_t dispatch_out(const T* x, int ldx, const T* w, const T* bias, void* y, int mc, int N, int K,
+                                int out_dtype, bool pdl, cudaStream_t stream, size_t y_off) {
+    if (out_dtype == ZL_F32)
+        return launch_dense<T, float>(x, ldx, w, bias, static_cast<float*>(y) + y_off, mc, N, K, pdl, stream);
+    return launch_dense<T, T>(x, ldx, w, bias, static_cast<T*>(y) + y_off, mc, N, K, pdl, stream);
+}
+
+}  // namespace zl
+
+using namespace zl;
+
+extern "C" int zl_dense_gemm_skinny(const void* x, int ldx, const void* w, const void* bias, void* y, int M,
+                                    int N, int K, int dtype, int out_dtype, int pdl, zl_stream_t stream) {
+    ZL_CHECK_ARG(x && w && y && M > 0 && N > 0 && K > 0);
+    ZL_CHECK_ARG(dtype == ZL_F16 || dtype == ZL_BF16);
+    ZL_CHECK_ARG(out_dtype == dtype || out_dtype == ZL_F32);
+    ZL_CHECK_SUPPORTED(K % 32 == 0);
+    ZL_CHECK_ARG(ldx >= K && ldx % 8 == 0);
+    ZL_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0);
+    for (int m0 = 0; m0 < M; m0 += 32) {
+        const int mc = (M - m0) < 32 ? (M - m0) : 32;
+        const bool use_pdl = pdl != 0 && m0 == 0;
+        cudaError_t e;
+        if (dtype == ZL_F16)
+            e = dispatch_out<__half>(static_cast<const __half*>(x) + (size_t)m0 * ldx, ldx,
+                                     static_cast<const __half*>(w), static_cast<const __half*>(bias), y, mc, N,
+                                     K, out_dtype, use_pdl, stream, (size_t)m0 * N);
+        else
+            e = dispatch_out<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(x) + (size_t)m0 * ldx, ldx,
+                                            static_cast<const __nv_bfloat16*>(w),
+                                            static_cast<const __nv_bfloat16*>(bias), y, mc, N, K, out_dtype,
+                                            use_pdl, stream, (size_t)m0 * N);
+        ZL_CHECK_CUDA(e);
+    }
+    return ZL_OK;
+}

@@ -1,0 +1,653 @@
+// Host-side decode driver (C++): weights, KV buffers, the per-step kernel chain and its CUDA graph.
+//
+// Stands in for model::LLaMA::encode / EncoderLayer::forward / Attention::dynamic_batch_forward /
+// FeedForward::forward at decode (reference src/model/llama.cpp:75-165, src/nn/block/block.cpp:86-143,
+// src/nn/attention/attention.cpp:846-964, src/nn/feedforward/feedforward.cpp:113-137) and for the
+// Int4GPTQ load pipeline (src/nn/linear/linear.cpp:1139-1244).  The reference launches ~12 kernels per
+// layer with no graph; here a layer is 8 launches chained with programmatic dependent launch inside one
+// CUDA graph per batch size.
+#include "common.cuh"
+#include "w4_layout.cuh"
+
+#include <map>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct Staged {
+    void* ptr = nullptr;
+    int rows = 0, cols = 0, elem = 0;
+};
+
+struct W4Lin {
+    void* packed = nullptr;
+    void* bias = nullptr;
+    int N = 0, K = 0;
+};
+struct DenseLin {
+    void* w = nullptr;
+    void* bias = nullptr;
+    int N = 0, K = 0;
+};
+
+struct Layer {
+    void* ln_attn = nullptr;
+    void* ln_ff = nullptr;
+    W4Lin q_qkv, q_o, q_gu, q_down;
+    DenseLin d_qkv, d_o, d_gu, d_down;
+    void* kbuf = nullptr;   // (max_batch, max_seq, Hkv, d)
+    void* vbuf = nullptr;
+    void** k_addrs = nullptr;   // device (max_batch)
+    void** v_addrs = nullptr;
+};
+
+}  // namespace
+
+struct zl_llama {
+    zl_llama_config_t cfg{};
+    cudaStream_t stream = nullptr;
+    std::map<std::string, Staged> staged;
+    std::vector<Layer> layers;
+    void* emb = nullptr;
+    void* lm_head = nullptr;
+    void* ln_f = nullptr;
+    bool lm_head_tied = false;
+    bool finalized = false;
+    // local (per-rank) sizes
+    int hq = 0, hkv = 0, ff = 0;
+    // activations
+    void *h = nullptr, *xn = nullptr, *qkv = nullptr, *q = nullptr, *ao = nullptr, *act = nullptr,
+         *pend = nullptr, *gu = nullptr;
+    float* logits = nullptr;
+    float *cosb = nullptr, *sinb = nullptr;
+    int32_t *d_tokens = nullptr, *d_pos = nullptr, *d_lens = nullptr, *d_next = nullptr, *d_iota = nullptr;
+    void* attn_ws = nullptr;
+    size_t attn_ws_bytes = 0;
+    void* argmax_ws = nullptr;
+    int32_t* h_stage = nullptr;   // pinned: tokens | pos | lens | next
+    std::map<int, cudaGraphExec_t> graphs;
+    double weight_bytes = 0;
+    int kernels_per_step = 0;
+};
+
+namespace {
+
+using namespace zl;
+
+#define RCHECK(expr)                \
+    do {                            \
+        int _rc = (expr);           \
+        if (_rc != ZL_OK) return _rc; \
+    } while (0)
+
+
+
+int dmalloc(void** p, size_t bytes) {
+    ZL_CHECK_CUDA(cudaMalloc(p, bytes ? bytes : 16));
+    return ZL_OK;
+}
+
+__global__ void k_lens_from_pos(const int32_t* __restrict__ pos, int32_t* __restrict__ lens, int B) {
+    pdl_trigger();
+    pdl_wait();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) lens[i] = pos[i] + 1;
+}
+__global__ void k_advance(int32_t* __restrict__ tokens, int32_t* __restrict__ pos, const int32_t* __restrict__ next,
+                          int B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) {
+        tokens[i] = next[i];
+        pos[i] += 1;
+    }
+}
+__global__ void k_iota(int32_t* p, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+__global__ void k_ptr_table(void** tab, char* base, size_t stride, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tab[i] = base + (size_t)i * stride;
+}
+__global__ void k_swiglu_row_map(int32_t* map, int F) {
+    // packed row p: 16-row tile = 8 gate rows then the 8 matching up rows (source = [gate(F); up(F)])
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < 2 * F) {
+        int tile = p >> 4, r = p & 15;
+        map[p] = (r < 8) ? tile * 8 + r : F + tile * 8 + (r - 8);
+    }
+}
+
+const Staged* find(const zl_llama* m, const std::string& name) {
+    auto it = m->staged.find(name);
+    return it == m->staged.end() ? nullptr : &it->second;
+}
+
+void drop(zl_llama* m, const std::string& name) {
+    auto it = m->staged.find(name);
+    if (it != m->staged.end()) {
+        cudaFree(it->second.ptr);
+        m->staged.erase(it);
+    }
+}
+
+// HF GPTQ/AWQ tensors of one Linear -> reference k-major tensors written at row offset n_off of the fused
+// k-major buffers (linear.cpp:1139-1160 preprocess_weight + 1085-1099 transpose_weight).
+int to_k_major(zl_llama* m, const std::string& prefix, int K, int N, uint32_t* qw_km, uint8_t* qz_km, __half* sc_km,
+               int n_off, int n_total) {
+    const Staged* qw = find(m, prefix + ".qweight");
+    const Staged* qz = find(m, prefix + ".qzeros");
+    const Staged* sc = find(m, prefix + ".scales");
+    if (!qw || !qz || !sc) {
+        zl_set_last_error(__FILE__, __LINE__, ("missing GPTQ tensors for " + prefix).c_str());
+        return ZL_ERR_STATE;
+    }
+    const int G = K / m->cfg.group_size;
+    const bool awq = m->cfg.quant_type == 6;
+    cudaStream_t st = m->stream;
+    uint32_t* w_kn = nullptr;   // (K/8, N)
+    if (awq) {
+        ZL_CHECK_ARG(qw->rows == K && qw->cols == N / 8);
+        RCHECK(dmalloc((void**)&w_kn, (size_t)(K / 8) * N * 4));
+        RCHECK(zl_awq_shuffle((const uint32_t*)qw->ptr, w_kn, K, N, 1, st));
+        RCHECK(zl_awq_un_shuffle((uint32_t*)qz->ptr, G, N / 8, st));
+    } else {
+        ZL_CHECK_ARG(qw->rows == K / 8 && qw->cols == N);
+        w_kn = (uint32_t*)qw->ptr;
+        RCHECK(zl_gptq_shuffle(w_kn, nullptr, nullptr, K, N, st));
+        RCHECK(zl_gptq_increase_zero((uint32_t*)qz->ptr, (size_t)G * (N / 8), st));
+    }
+    ZL_CHECK_ARG(qz->rows == G && qz->cols == N / 8 && sc->rows == G && sc->cols == N);
+    uint8_t* z8 = nullptr;   // (G, N)
+    RCHECK(dmalloc((void**)&z8, (size_t)G * N));
+    RCHECK(zl_q4_to_q8((const uint32_t*)qz->ptr, z8, (size_t)G * (N / 8), st));
+    // transposes straight into the fused buffers (row offset n_off)
+    RCHECK(zl_transpose_2d(w_kn, qw_km + (size_t)n_off * (K / 8), K / 8, N, 4, st));
+    RCHECK(zl_transpose_2d(z8, qz_km + (size_t)n_off * G, G, N, 1, st));
+    RCHECK(zl_transpose_2d(sc->ptr, sc_km + (size_t)n_off * G, G, N, 2, st));
+    ZL_CHECK_CUDA(cudaStreamSynchronize(st));
+    cudaFree(z8);
+    if (awq) cudaFree(w_kn);
+    (void)n_total;
+    return ZL_OK;
+}
+
+int build_w4(zl_llama* m, const std::vector<std::string>& prefixes, const std::vector<int>& ns, int K, bool swiglu,
+             W4Lin* out) {
+    int N = 0;
+    for (int n : ns) N += n;
+    const int G = K / m->cfg.group_size;
+    uint32_t* qw_km = nullptr;
+    uint8_t* qz_km = nullptr;
+    __half* sc_km = nullptr;
+    RCHECK(dmalloc((void**)&qw_km, (size_t)N * (K / 8) * 4));
+    RCHECK(dmalloc((void**)&qz_km, (size_t)N * G));
+    RCHECK(dmalloc((void**)&sc_km, (size_t)N * G * 2));
+    int off = 0;
+    bool any_bias = false;
+    for (size_t i = 0; i < prefixes.size(); ++i) {
+        RCHECK(to_k_major(m, prefixes[i], K, ns[i], qw_km, qz_km, sc_km, off, N));
+        if (find(m, prefixes[i] + ".bias")) any_bias = true;
+        off += ns[i];
+    }
+    int32_t* row_map = nullptr;
+    if (swiglu) {
+        RCHECK(dmalloc((void**)&row_map, (size_t)N * 4));
+        k_swiglu_row_map<<<cdiv(N, 256), 256, 0, m->stream>>>(row_map, N / 2);
+        ZL_CHECK_LAUNCH();
+    }
+    const size_t pbytes = zl_w4_packed_bytes(N, K, m->cfg.group_size);
+    ZL_CHECK_SUPPORTED(pbytes > 0);
+    RCHECK(dmalloc(&out->packed, pbytes));
+    RCHECK(zl_w4_pack(qw_km, qz_km, sc_km, row_map, out->packed, N, K, m->cfg.group_size, m->cfg.sym, m->stream));
+    if (any_bias && !swiglu) {
+        RCHECK(dmalloc(&out->bias, (size_t)N * 2));
+        ZL_CHECK_CUDA(cudaMemsetAsync(out->bias, 0, (size_t)N * 2, m->stream));
+        off = 0;
+        for (size_t i = 0; i < prefixes.size(); ++i) {
+            const Staged* b = find(m, prefixes[i] + ".bias");
+            if (b)
+                ZL_CHECK_CUDA(cudaMemcpyAsync((char*)out->bias + (size_t)off * 2, b->ptr, (size_t)ns[i] * 2,
+                                              cudaMemcpyDeviceToDevice, m->stream));
+            off += ns[i];
+        }
+    }
+    ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+    cudaFree(qw_km);
+    cudaFree(qz_km);
+    cudaFree(sc_km);
+    if (row_map) cudaFree(row_map);
+    for (auto& p : prefixes) {
+        drop(m, p + ".qweight");
+        drop(m, p + ".qzeros");
+        drop(m, p + ".scales");
+        drop(m, p + ".g_idx");
+        drop(m, p + ".bias");
+    }
+    out->N = N;
+    out->K = K;
+    m->weight_bytes += (double)pbytes;
+    return ZL_OK;
+}
+
+int build_dense(zl_llama* m, const std::vector<std::string>& prefixes, const std::vector<int>& ns, int K,
+                DenseLin* out) {
+    int N = 0;
+    for (int n : ns) N += n;
+    RCHECK(dmalloc(&out->w, (size_t)N * K * 2));
+    int off = 0;
+    bool any_bias = false;
+    for (size_t i = 0; i < prefixes.size(); ++i) {
+        const Staged* w = find(m, prefixes[i] + ".weight");
+        if (!w || w->rows != ns[i] || w->cols != K) {
+            zl_set_last_error(__FILE__, __LINE__, ("missing/ill-shaped dense weight " + prefixes[i]).c_str());
+            return ZL_ERR_STATE;
+        }
+        ZL_CHECK_CUDA(cudaMemcpyAsync((char*)out->w + (size_t)off * K * 2, w->ptr, (size_t)ns[i] * K * 2,
+                                      cudaMemcpyDeviceToDevice, m->stream));
+        if (find(m, prefixes[i] + ".bias")) any_bias = true;
+        off += ns[i];
+    }
+    if (any_bias) {
+        RCHECK(dmalloc(&out->bias, (size_t)N * 2));
+        ZL_CHECK_CUDA(cudaMemsetAsync(out->bias, 0, (size_t)N * 2, m->stream));
+        off = 0;
+        for (size_t i = 0; i < prefixes.size(); ++i) {
+            const Staged* b = find(m, prefixes[i] + ".bias");
+            if (b)
+                ZL_CHECK_CUDA(cudaMemcpyAsync((char*)out->bias + (size_t)off * 2, b->ptr, (size_t)ns[i] * 2,
+                                              cudaMemcpyDeviceToDevice, m->stream));
+            off += ns[i];
+        }
+    }
+    ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+    for (auto& p : prefixes) {
+        drop(m, p + ".weight");
+        drop(m, p + ".bias");
+    }
+    out->N = N;
+    out->K = K;
+    m->weight_bytes += (double)N * K * 2;
+    return ZL_OK;
+}
+
+int take_vector(zl_llama* m, const std::string& name, int n, void** out) {
+    auto it = m->staged.find(name);
+    if (it == m->staged.end() || (size_t)it->second.rows * it->second.cols != (size_t)n) {
+        zl_set_last_error(__FILE__, __LINE__, ("missing/ill-shaped tensor " + name).c_str());
+        return ZL_ERR_STATE;
+    }
+    *out = it->second.ptr;
+    m->staged.erase(it);
+    m->weight_bytes += (double)n * 2;
+    return ZL_OK;
+}
+
+int finalize_layer(zl_llama* m, int l) {
+    const auto& c = m->cfg;
+    Layer& L = m->layers[l];
+    const std::string p = "layers." + std::to_string(l) + ".";
+    const int D = c.dim_model, d = c.dim_head;
+    RCHECK(take_vector(m, p + "ln_attn.weight", D, &L.ln_attn));
+    RCHECK(take_vector(m, p + "ln_ff.weight", D, &L.ln_ff));
+    const std::vector<std::string> qkv = {p + "attn.project_q", p + "attn.project_k", p + "attn.project_v"};
+    const std::vector<int> qkv_n = {m->hq * d, m->hkv * d, m->hkv * d};
+    const std::vector<std::string> gu = {p + "ff.w_in", p + "ff.w_gated"};
+    const std::vector<int> gu_n = {m->ff, m->ff};
+    if (c.quant_type == 5 || c.quant_type == 6) {
+        RCHECK(build_w4(m, qkv, qkv_n, D, false, &L.q_qkv));
+        RCHECK(build_w4(m, {p + "attn.attn_out"}, {D}, m->hq * d, false, &L.q_o));
+        RCHECK(build_w4(m, gu, gu_n, D, true, &L.q_gu));
+        RCHECK(build_w4(m, {p + "ff.w_out"}, {D}, m->ff, false, &L.q_down));
+    } else {
+        RCHECK(build_dense(m, qkv, qkv_n, D, &L.d_qkv));
+        RCHECK(build_dense(m, {p + "attn.attn_out"}, {D}, m->hq * d, &L.d_o));
+        RCHECK(build_dense(m, gu, gu_n, D, &L.d_gu));
+        RCHECK(build_dense(m, {p + "ff.w_out"}, {D}, m->ff, &L.d_down));
+    }
+    return ZL_OK;
+}
+
+int finalize_globals(zl_llama* m) {
+    const auto& c = m->cfg;
+    RCHECK(take_vector(m, "token_embedding.weight", c.vocab_size * c.dim_model, &m->emb));
+    m->weight_bytes -= (double)c.vocab_size * c.dim_model * 2;   // the embedding table is gathered, not streamed
+    RCHECK(take_vector(m, "output_layernorm.weight", c.dim_model, &m->ln_f));
+    if (find(m, "lm_head.weight")) {
+        RCHECK(take_vector(m, "lm_head.weight", c.vocab_size * c.dim_model, &m->lm_head));
+    } else {
+        m->lm_head = m->emb;   // tied (Llama-3.2-1B)
+        m->lm_head_tied = true;
+        m->weight_bytes += (double)c.vocab_size * c.dim_model * 2;
+    }
+    return ZL_OK;
+}
+
+int alloc_runtime(zl_llama* m) {
+    const auto& c = m->cfg;
+    const int B = c.max_batch, D = c.dim_model, d = c.dim_head;
+    const size_t kv_task = (size_t)c.max_seq * m->hkv * d * 2;
+    for (auto& L : m->layers) {
+        RCHECK(dmalloc(&L.kbuf, kv_task * B));
+        RCHECK(dmalloc(&L.vbuf, kv_task * B));
+        RCHECK(dmalloc((void**)&L.k_addrs, sizeof(void*) * B));
+        RCHECK(dmalloc((void**)&L.v_addrs, sizeof(void*) * B));
+        k_ptr_table<<<1, 256, 0, m->stream>>>(L.k_addrs, (char*)L.kbuf, kv_task, B);
+        k_ptr_table<<<1, 256, 0, m->stream>>>(L.v_addrs, (char*)L.vbuf, kv_task, B);
+        ZL_CHECK_LAUNCH();
+    }
+    RCHECK(dmalloc(&m->h, (size_t)B * D * 2));
+    RCHECK(dmalloc(&m->xn, (size_t)B * D * 2));
+    RCHECK(dmalloc(&m->pend, (size_t)B * D * 2));
+    RCHECK(dmalloc(&m->qkv, (size_t)B * (m->hq + 2 * m->hkv) * d * 2));
+    RCHECK(dmalloc(&m->q, (size_t)B * m->hq * d * 2));
+    RCHECK(dmalloc(&m->ao, (size_t)B * m->hq * d * 2));
+    RCHECK(dmalloc(&m->gu, (size_t)B * 2 * m->ff * 2));
+    RCHECK(dmalloc(&m->act, (size_t)B * m->ff * 2));
+    RCHECK(dmalloc((void**)&m->logits, (size_t)B * c.vocab_size * 4));
+    RCHECK(dmalloc((void**)&m->cosb, (size_t)B * d * 4));
+    RCHECK(dmalloc((void**)&m->sinb, (size_t)B * d * 4));
+    RCHECK(dmalloc((void**)&m->d_tokens, B * 4));
+    RCHECK(dmalloc((void**)&m->d_pos, B * 4));
+    RCHECK(dmalloc((void**)&m->d_lens, B * 4));
+    RCHECK(dmalloc((void**)&m->d_next, B * 4));
+    RCHECK(dmalloc((void**)&m->d_iota, B * 4));
+    k_iota<<<1, 256, 0, m->stream>>>(m->d_iota, B);
+    ZL_CHECK_LAUNCH();
+    m->attn_ws_bytes = zl_decode_attention_workspace_bytes(B, 1, m->hq, d, c.max_seq);
+    RCHECK(dmalloc(&m->attn_ws, m->attn_ws_bytes));
+    RCHECK(dmalloc(&m->argmax_ws, zl_argmax_workspace_bytes(B)));
+    ZL_CHECK_CUDA(cudaMallocHost((void**)&m->h_stage, sizeof(int32_t) * 4 * B));
+    ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+    return ZL_OK;
+}
+
+// The decode-step kernel chain (captured into a graph by run_step).
+int enqueue_step(zl_llama* m, int B) {
+    const auto& c = m->cfg;
+    const int D = c.dim_model, d = c.dim_head, dt = c.dtype, pdl = c.use_pdl;
+    cudaStream_t st = m->stream;
+    const bool w4 = c.quant_type == 5 || c.quant_type == 6;
+    const float scale = 1.0f / sqrtf((float)d);   // attention.cpp:89
+
+    ZL_CHECK_CUDA(launch(k_lens_from_pos, dim3(cdiv(B, 64)), dim3(64), 0, st, false, (const int32_t*)m->d_pos,
+                         m->d_lens, B));
+    RCHECK(zl_rope_cos_sin(m->d_pos, m->cosb, m->sinb, B, d, c.rope_theta, c.rope_llama3_factor,
+                           c.rope_low_freq_factor, c.rope_high_freq_factor, c.rope_orig_ctx, 1, st));
+    RCHECK(zl_embedding(m->d_tokens, m->emb, m->h, B, D, c.vocab_size, dt, 0, st));
+    for (int l = 0; l < c.num_layers; ++l) {
+        Layer& L = m->layers[l];
+        if (w4) {
+            RCHECK(zl_rmsnorm(m->h, L.ln_attn, m->xn, B, D, c.eps, 1.f, dt, pdl, st));
+            RCHECK(zl_w4a16_gemm(m->xn, D, L.q_qkv.packed, L.q_qkv.bias, nullptr, m->qkv, B, L.q_qkv.N, D,
+                                 c.group_size, ZL_EPI_NONE, pdl, st));
+        } else {
+            // residual of the previous layer's FFN is folded into this norm (block.cpp:139-141 + 131)
+            RCHECK(zl_add_rmsnorm(m->h, l == 0 ? nullptr : m->pend, L.ln_attn, m->h, m->xn, B, D, c.eps, 1.f, 0, dt,
+                                  pdl, st));
+            RCHECK(zl_dense_gemm_skinny(m->xn, D, L.d_qkv.w, L.d_qkv.bias, m->qkv, B, L.d_qkv.N, D, dt, dt, pdl,
+                                        st));
+        }
+        RCHECK(zl_qkv_rope_append(m->cosb, m->sinb, m->qkv, m->q, m->d_iota, m->d_pos, L.k_addrs, L.v_addrs, B,
+                                  m->hq, m->hkv, d, 1, 1, m->d_lens, dt, pdl, st));
+        RCHECK(zl_decode_attention(m->q, m->d_lens, L.k_addrs, L.v_addrs, nullptr, scale, c.max_seq, m->ao, B, 1,
+                                   m->hq, m->hkv, d, 1, m->attn_ws, m->attn_ws_bytes, dt, pdl, st));
+        if (w4) {
+            RCHECK(zl_w4a16_gemm(m->ao, m->hq * d, L.q_o.packed, L.q_o.bias, m->h, m->h, B, D, m->hq * d,
+                                 c.group_size, ZL_EPI_RESIDUAL, pdl, st));
+            RCHECK(zl_rmsnorm(m->h, L.ln_ff, m->xn, B, D, c.eps, 1.f, dt, pdl, st));
+            RCHECK(zl_w4a16_gemm(m->xn, D, L.q_gu.packed, nullptr, nullptr, m->act, B, L.q_gu.N, D, c.group_size,
+                                 ZL_EPI_SWIGLU, pdl, st));
+            RCHECK(zl_w4a16_gemm(m->act, m->ff, L.q_down.packed, L.q_down.bias, m->h, m->h, B, D, m->ff,
+                                 c.group_size, ZL_EPI_RESIDUAL, pdl, st));
+        } else {
+            RCHECK(zl_dense_gemm_skinny(m->ao, m->hq * d, L.d_o.w, L.d_o.bias, m->pend, B, D, m->hq * d, dt, dt, pdl,
+                                        st));
+            RCHECK(zl_add_rmsnorm(m->h, m->pend, L.ln_ff, m->h, m->xn, B, D, c.eps, 1.f, 0, dt, pdl, st));
+            RCHECK(zl_dense_gemm_skinny(m->xn, D, L.d_gu.w, L.d_gu.bias, m->gu, B, 2 * m->ff, D, dt, dt, pdl, st));
+            RCHECK(zl_gate_mul(m->gu, 2 * m->ff, (char*)m->gu + (size_t)m->ff * 2, 2 * m->ff, m->act, m->ff, B,
+                               m->ff, 0, dt, st));
+            RCHECK(zl_dense_gemm_skinny(m->act, m->ff, L.d_down.w, L.d_down.bias, m->pend, B, D, m->ff, dt, dt, pdl,
+                                        st));
+        }
+    }
+    if (w4) {
+        RCHECK(zl_rmsnorm(m->h, m->ln_f, m->xn, B, D, c.eps, 1.f, dt, pdl, st));
+    } else {
+        RCHECK(zl_add_rmsnorm(m->h, m->pend, m->ln_f, m->h, m->xn, B, D, c.eps, 1.f, 0, dt, pdl, st));
+    }
+    RCHECK(zl_dense_gemm_skinny(m->xn, D, m->lm_head, nullptr, m->logits, B, c.vocab_size, D, dt, ZL_F32, pdl, st));
+    RCHECK(zl_argmax(m->logits, m->d_next, B, c.vocab_size, m->argmax_ws, zl_argmax_workspace_bytes(B), pdl, st));
+    return ZL_OK;
+}
+
+int run_step(zl_llama* m, int B) {
+    if (!m->cfg.use_graph) return enqueue_step(m, B);
+    auto it = m->graphs.find(B);
+    if (it == m->graphs.end()) {
+        cudaGraph_t graph = nullptr;
+        ZL_CHECK_CUDA(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
+        const long long before = zl_launch_count(0);
+        int rc = enqueue_step(m, B);
+        const long long after = zl_launch_count(0);
+        cudaError_t ce = cudaStreamEndCapture(m->stream, &graph);
+        if (rc != ZL_OK) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        ZL_CHECK_CUDA(ce);
+        cudaGraphExec_t exec = nullptr;
+        ZL_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        size_t n_nodes = 0;
+        cudaGraphGetNodes(graph, nullptr, &n_nodes);
+        m->kernels_per_step = (int)n_nodes;
+        (void)before;
+        (void)after;
+        cudaGraphDestroy(graph);
+        it = m->graphs.emplace(B, exec).first;
+    }
+    ZL_CHECK_CUDA(cudaGraphLaunch(it->second, m->stream));
+    return ZL_OK;
+}
+
+}  // namespace
+
+extern "C" int zl_llama_create(const zl_llama_config_t* cfg, zl_llama_t** out) {
+    ZL_CHECK_ARG(cfg && out);
+    ZL_CHECK_ARG(cfg->num_layers > 0 && cfg->dim_model > 0 && cfg->num_heads > 0 && cfg->num_kv_heads > 0);
+    ZL_CHECK_ARG(cfg->dim_head > 0 && cfg->dim_ff > 0 && cfg->vocab_size > 0 && cfg->max_batch > 0 &&
+                 cfg->max_seq > 0);
+    ZL_CHECK_SUPPORTED(cfg->quant_type == 0 || cfg->quant_type == 5 || cfg->quant_type == 6);
+    ZL_CHECK_SUPPORTED(cfg->quant_type == 0 || cfg->dtype == ZL_F16);   // "A must be half" q_gemm_k_major.cu:989
+    ZL_CHECK_SUPPORTED(cfg->dtype == ZL_F16 || cfg->dtype == ZL_BF16);
+    ZL_CHECK_SUPPORTED(cfg->tp_size >= 1 && cfg->tp_rank >= 0 && cfg->tp_rank < cfg->tp_size);
+    ZL_CHECK_SUPPORTED(cfg->tp_size == 1);   // TP goes through zl_comm; not wired in the driver yet
+    ZL_CHECK_SUPPORTED(cfg->quant_type == 0 || cfg->group_size == zl::kW4GroupK);
+    zl_llama* m = new zl_llama();
+    m->cfg = *cfg;
+    m->hq = cfg->num_heads / cfg->tp_size;
+    m->hkv = cfg->num_kv_heads / cfg->tp_size;
+    m->ff = cfg->dim_ff / cfg->tp_size;
+    m->layers.resize(cfg->num_layers);
+    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete m;
+        zl_set_last_error(__FILE__, __LINE__, "cudaStreamCreate failed (no CUDA device? there is no CPU fallback)");
+        return ZL_ERR_CUDA;
+    }
+    *out = m;
+    return ZL_OK;
+}
+
+extern "C" void zl_llama_destroy(zl_llama_t* m) {
+    if (!m) return;
+    cudaStreamSynchronize(m->stream);
+    for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);
+    for (auto& s : m->staged) cudaFree(s.second.ptr);
+    for (auto& L : m->layers) {
+        for (void* p : {L.ln_attn, L.ln_ff, L.q_qkv.packed, L.q_qkv.bias, L.q_o.packed, L.q_o.bias, L.q_gu.packed,
+                        L.q_down.packed, L.q_down.bias, L.d_qkv.w, L.d_qkv.bias, L.d_o.w, L.d_o.bias, L.d_gu.w,
+                        L.d_gu.bias, L.d_down.w, L.d_down.bias, L.kbuf, L.vbuf, (void*)L.k_addrs, (void*)L.v_addrs})
+            if (p) cudaFree(p);
+    }
+    for (void* p : {m->emb, m->lm_head_tied ? nullptr : m->lm_head, m->ln_f, m->h, m->xn, m->qkv, m->q, m->ao, m->act,
+                    m->pend, m->gu, (void*)m->logits, (void*)m->cosb, (void*)m->sinb, (void*)m->d_tokens,
+                    (void*)m->d_pos, (void*)m->d_lens, (void*)m->d_next, (void*)m->d_iota, m->attn_ws, m->argmax_ws})
+        if (p) cudaFree(p);
+    if (m->h_stage) cudaFreeHost(m->h_stage);
+    cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+extern "C" int zl_llama_load_tensor(zl_llama_t* m, const char* name, const void* data_host, int rows, int cols,
+                                    int elem_bytes) {
+    ZL_CHECK_ARG(m && name && data_host && rows > 0 && cols > 0 && elem_bytes > 0);
+    if (m->finalized) {
+        zl_set_last_error(__FILE__, __LINE__, "model already finalized");
+        return ZL_ERR_STATE;
+    }
+    Staged s;
+    s.rows = rows;
+    s.cols = cols;
+    s.elem = elem_bytes;
+    const size_t bytes = (size_t)rows * cols * elem_bytes;
+    RCHECK(dmalloc(&s.ptr, bytes));
+    ZL_CHECK_CUDA(cudaMemcpyAsync(s.ptr, data_host, bytes, cudaMemcpyHostToDevice, m->stream));
+    ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+    drop(m, name);
+    m->staged[name] = s;
+    return ZL_OK;
+}
+
+extern "C" int zl_llama_finalize(zl_llama_t* m) {
+    ZL_CHECK_ARG(m);
+    if (m->finalized) return ZL_OK;
+    for (int l = 0; l < m->cfg.num_layers; ++l)
+        if (!m->layers[l].ln_attn) RCHECK(finalize_layer(m, l));
+    RCHECK(finalize_globals(m));
+    RCHECK(alloc_runtime(m));
+    m->finalized = true;
+    return ZL_OK;
+}
+
+namespace {
+int stage_random(zl_llama* m, const std::string& name, int rows, int cols, int elem, int kind, float lo, float hi,
+                 uint64_t seed) {
+    Staged s;
+    s.rows = rows;
+    s.cols = cols;
+    s.elem = elem;
+    const size_t n = (size_t)rows * cols;
+    RCHECK(dmalloc(&s.ptr, n * elem));
+    uint64_t h = seed;
+    for (char ch : name) h = h * 1099511628211ull + (unsigned char)ch;
+    if (kind == 0)
+        RCHECK(zl_fill_random_u32((uint32_t*)s.ptr, n, h, m->stream));
+    else if (kind == 1)
+        RCHECK(zl_fill_const_u32((uint32_t*)s.ptr, n, 0x77777777u, m->stream));
+    else
+        RCHECK(zl_fill_uniform(s.ptr, n, lo, hi, h, m->cfg.dtype, m->stream));
+    m->staged[name] = s;
+    return ZL_OK;
+}
+
+int stage_random_linear(zl_llama* m, const std::string& prefix, int K, int N, uint64_t seed) {
+    const auto& c = m->cfg;
+    if (c.quant_type == 5) {
+        const int G = K / c.group_size;
+        RCHECK(stage_random(m, prefix + ".qweight", K / 8, N, 4, 0, 0, 0, seed));
+        RCHECK(stage_random(m, prefix + ".qzeros", G, N / 8, 4, c.sym ? 1 : 0, 0, 0, seed));
+        RCHECK(stage_random(m, prefix + ".scales", G, N, 2, 2, 0.002f, 0.006f, seed));
+    } else if (c.quant_type == 6) {
+        const int G = K / c.group_size;
+        RCHECK(stage_random(m, prefix + ".qweight", K, N / 8, 4, 0, 0, 0, seed));
+        RCHECK(stage_random(m, prefix + ".qzeros", G, N / 8, 4, 0, 0, 0, seed));
+        RCHECK(stage_random(m, prefix + ".scales", G, N, 2, 2, 0.002f, 0.006f, seed));
+    } else {
+        RCHECK(stage_random(m, prefix + ".weight", N, K, 2, 2, -0.035f, 0.035f, seed));   // ~ randn*0.02
+    }
+    return ZL_OK;
+}
+}  // namespace
+
+extern "C" int zl_llama_init_synthetic(zl_llama_t* m, uint64_t seed) {
+    ZL_CHECK_ARG(m);
+    if (m->finalized) {
+        zl_set_last_error(__FILE__, __LINE__, "model already finalized");
+        return ZL_ERR_STATE;
+    }
+    const auto& c = m->cfg;
+    const int D = c.dim_model, d = c.dim_head;
+    for (int l = 0; l < c.num_layers; ++l) {
+        const std::string p = "layers." + std::to_string(l) + ".";
+        RCHECK(stage_random(m, p + "ln_attn.weight", 1, D, 2, 2, 0.9f, 1.1f, seed));
+        RCHECK(stage_random(m, p + "ln_ff.weight", 1, D, 2, 2, 0.9f, 1.1f, seed));
+        RCHECK(stage_random_linear(m, p + "attn.project_q", D, m->hq * d, seed));
+        RCHECK(stage_random_linear(m, p + "attn.project_k", D, m->hkv * d, seed));
+        RCHECK(stage_random_linear(m, p + "attn.project_v", D, m->hkv * d, seed));
+        RCHECK(stage_random_linear(m, p + "attn.attn_out", m->hq * d, D, seed));
+        RCHECK(stage_random_linear(m, p + "ff.w_in", D, m->ff, seed));
+        RCHECK(stage_random_linear(m, p + "ff.w_gated", D, m->ff, seed));
+        RCHECK(stage_random_linear(m, p + "ff.w_out", m->ff, D, seed));
+        RCHECK(finalize_layer(m, l));   // bound the staging memory to one layer
+    }
+    RCHECK(stage_random(m, "token_embedding.weight", c.vocab_size, D, 2, 2, -0.035f, 0.035f, seed));
+    RCHECK(stage_random(m, "output_layernorm.weight", 1, D, 2, 2, 0.9f, 1.1f, seed));
+    RCHECK(stage_random(m, "lm_head.weight", c.vocab_size, D, 2, 2, -0.035f, 0.035f, seed));
+    return zl_llama_finalize(m);
+}
+
+extern "C" int zl_llama_set_state(zl_llama_t* m, const int32_t* tokens_host, const int32_t* positions_host,
+                                  int B) {
+    ZL_CHECK_ARG(m && tokens_host && positions_host && B > 0 && B <= m->cfg.max_batch);
+    if (!m->finalized) {
+        zl_set_last_error(__FILE__, __LINE__, "model not finalized");
+        return ZL_ERR_STATE;
+    }
+    for (int i = 0; i < B; ++i) {
+        ZL_CHECK_ARG(positions_host[i] >= 0 && positions_host[i] < m->cfg.max_seq);
+        m->h_stage[i] = tokens_host[i];
+        m->h_stage[B + i] = positions_host[i];
+    }
+    ZL_CHECK_CUDA(cudaMemcpyAsync(m->d_tokens, m->h_stage, B * 4, cudaMemcpyHostToDevice, m->stream));
+    ZL_CHECK_CUDA(cudaMemcpyAsync(m->d_pos, m->h_stage + B, B * 4, cudaMemcpyHostToDevice, m->stream));
+    return ZL_OK;
+}
+
+extern "C" int zl_llama_step_device(zl_llama_t* m, int B) {
+    ZL_CHECK_ARG(m && B > 0 && B <= m->cfg.max_batch);
+    RCHECK(run_step(m, B));
+    k_advance<<<cdiv(B, 64), 64, 0, m->stream>>>(m->d_tokens, m->d_pos, m->d_next, B);
+    ZL_CHECK_LAUNCH();
+    return ZL_OK;
+}
+
+extern "C" int zl_llama_decode(zl_llama_t* m, const int32_t* tokens_host, const int32_t* positions_host, int B,
+                               int32_t* next_tokens_host, float* logits_host) {
+    ZL_CHECK_ARG(next_tokens_host != nullptr);
+    RCHECK(zl_llama_set_state(m, tokens_host, positions_host, B));
+    RCHECK(run_step(m, B));
+    ZL_CHECK_CUDA(cudaMemcpyAsync(m->h_stage + 3 * B, m->d_next, B * 4, cudaMemcpyDeviceToHost, m->stream));
+    if (logits_host)
+        ZL_CHECK_CUDA(cudaMemcpyAsync(logits_host, m->logits, (size_t)B * m->cfg.vocab_size * 4,
+                                      cudaMemcpyDeviceToHost, m->stream));
+    ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+    for (int i = 0; i < B; ++i) next_tokens_host[i] = m->h_stage[3 * B + i];
+    return ZL_OK;
+}
+
+extern "C" int zl_llama_sync(zl_llama_t* m) {
+    ZL_CHECK_ARG(m);
+    ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+    return ZL_OK;
+}
+
+extern "C" zl_stream_t zl_llama_stream(zl_llama_t* m) { return m ? (zl_stream_t)m->stream : nullptr; }
+
+extern "C" int zl_llama_stats(zl_llama_t* m, int B, double* weight_bytes, int* kernels_per_step) {
+    ZL_CHECK_ARG(m);
+    (void)B;
+    if (weight_bytes) *weight_bytes = m->weight_bytes;
+    if (kernels_per_step) *kernels_per_step = m->kernels_per_step;
+    return ZL_OK;
+}

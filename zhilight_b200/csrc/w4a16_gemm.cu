@@ -1,0 +1,275 @@
+// W4A16 skinny GEMM (decode, M <= 32 per pass) on the ZLW4 layout -- warp-MMA variant.
+//
+// Replaces nn::gptq::gptq_gemm_k_major's GEMV path KERNEL_gemm_warp_reduce and the fused gate-in
+// kernel (reference src/nn/quant/gptq/q_gemm_k_major.cu:176-237, 529-578, 957-1116).
+//
+// Design:
+//   * grid = N/32 CTAs (one 32-row super-tile each), 8 warps; warp w owns a contiguous range of
+//     k-groups and streams its 2128-byte ZLW4 blocks through a private 4-stage shared-memory ring
+//     with 1-D bulk-TMA copies (cp.async.bulk -> SASS UBLKCP) completing on per-stage mbarriers.
+//     Warps never synchronise with each other in the main loop.
+//   * the first ring fill is issued BEFORE griddepcontrol.wait, so under programmatic dependent
+//     launch the weight stream of GEMM i+1 is already in flight while GEMM i drains.
+//   * dequant: lop3 0x6400 magic-number trick gives exact (q - z) in fp16; weights are the A operand
+//     of mma.sync.m16n8k16 (rows = output features), activations the B operand (cols = tokens);
+//     fp32 accumulation per group, then acc += scale * acc_group in fp32 (the group scale never
+//     touches fp16, unlike the reference's fp16 8-product partial sums).
+//   * epilogue: cross-warp (split-k) reduction through shared memory, then bias / SwiGLU / residual.
+#include "common.cuh"
+#include "w4_layout.cuh"
+
+namespace zl {
+
+constexpr int kW4Warps = 8;
+constexpr int kW4Stages = 4;
+constexpr int kW4SmemBytes = kW4Warps * kW4Stages * kW4BlockBytes + kW4Warps * kW4Stages * 8;
+
+template <int NT>
+__device__ __forceinline__ void load_bfrag(uint4 (&b)[NT][4], const __half* __restrict__ x, int ldx, int mc,
+                                           int kbase, int g, int t) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const int tok = nt * 8 + g;
+        if (tok < mc) {
+            const __half* p = x + (size_t)tok * ldx + kbase + t * 8;
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) b[nt][ii] = ld_cg_u4(p + ii * 32);
+        } else {
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) b[nt][ii] = make_uint4(0, 0, 0, 0);
+        }
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(kW4Warps * 32)
+k_w4a16_mma(const __half* __restrict__ x, int ldx, const uint8_t* __restrict__ packed,
+            const __half* __restrict__ bias, const __half* __restrict__ residual, __half* __restrict__ y,
+            int mc, int N, int K, int epi) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int st = blockIdx.x;
+    const int G = K / kW4GroupK;
+    const int g_begin = (warp * G) / kW4Warps;
+    const int g_end = ((warp + 1) * G) / kW4Warps;
+    const int ng = g_end - g_begin;
+
+    uint8_t* ring = smem + warp * (kW4Stages * kW4BlockBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kW4Warps * kW4Stages * kW4BlockBytes) + warp * kW4Stages;
+    const uint8_t* gsrc = packed + ((size_t)st * G + g_begin) * kW4BlockBytes;
+
+    pdl_trigger();
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kW4Stages; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+#pragma unroll
+        for (int s = 0; s < kW4Stages; ++s) {
+            if (s < ng) {
+                mbar_expect_tx(&bars[s], kW4BlockBytes);
+                bulk_g2s(ring + s * kW4BlockBytes, gsrc + (size_t)s * kW4BlockBytes, kW4BlockBytes, &bars[s]);
+            }
+        }
+    }
+    __syncwarp();
+    // everything above only touched read-only weights; activations come from the predecessor kernel
+    pdl_wait();
+
+    float acc[2][NT][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < NT; ++b)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+
+    constexpr bool kPrefetchB = (NT <= 2);
+    uint4 bfr[NT][4];
+    if (kPrefetchB && ng > 0) load_bfrag<NT>(bfr, x, ldx, mc, g_begin * kW4GroupK, g, t);
+
+    const __half2 one16 = __half2half2(__ushort_as_half((unsigned short)0x2c00));   // 1/16
+    const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
+
+    for (int i = 0; i < ng; ++i) {
+        const int s = i % kW4Stages;
+        const uint32_t parity = (uint32_t)(i / kW4Stages) & 1u;
+        uint4 bcur[NT][4];
+        if (kPrefetchB) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) bcur[nt][ii] = bfr[nt][ii];
+            if (i + 1 < ng) load_bfrag<NT>(bfr, x, ldx, mc, (g_begin + i + 1) * kW4GroupK, g, t);
+        } else {
+            load_bfrag<NT>(bcur, x, ldx, mc, (g_begin + i) * kW4GroupK, g, t);
+        }
+
+        mbar_wait(&bars[s], parity);
+        const uint8_t* blk = ring + s * kW4BlockBytes;
+
+#pragma unroll
+        for (int tt = 0; tt < 2; ++tt) {
+            const __half2 sc = *reinterpret_cast<const __half2*>(blk + kW4ScaleOff + (tt * 8 + g) * 4);
+            const uint32_t zz = blk[kW4ZeroOff + tt * 8 + g];
+            // -(1024 + z_g) and -(64 + z_{g+8}) as exact fp16 bit patterns (q_gemm_k_major.cu:52-61)
+            const __half2 z1 = __half2half2(__ushort_as_half((unsigned short)(0xe400u | (zz & 0xFu))));
+            const __half2 z16 = __half2half2(__ushort_as_half((unsigned short)(0xd400u | (zz & 0xF0u))));
+            float accg[NT][4];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const uint4 wv = *reinterpret_cast<const uint4*>(blk + ((tt * 2 + hh) * 32 + lane) * 16);
+                const uint32_t wj[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = hh * 4 + jj;
+                    uint32_t w = wj[jj];
+                    uint32_t a[4];
+                    uint32_t p0 = lop3_and_or<0x000f000fu, 0x64006400u>(w);
+                    uint32_t p1 = lop3_and_or<0x00f000f0u, 0x64006400u>(w);
+                    w >>= 8;
+                    uint32_t p2 = lop3_and_or<0x000f000fu, 0x64006400u>(w);
+                    uint32_t p3 = lop3_and_or<0x00f000f0u, 0x64006400u>(w);
+                    __half2 h0 = __hadd2(*reinterpret_cast<__half2*>(&p0), z1);
+                    __half2 h1 = __hfma2(*reinterpret_cast<__half2*>(&p1), one16, z16);
+                    __half2 h2 = __hadd2(*reinterpret_cast<__half2*>(&p2), z1);
+                    __half2 h3 = __hfma2(*reinterpret_cast<__half2*>(&p3), one16, z16);
+                    a[0] = *reinterpret_cast<uint32_t*>(&h0);
+                    a[1] = *reinterpret_cast<uint32_t*>(&h1);
+                    a[2] = *reinterpret_cast<uint32_t*>(&h2);
+                    a[3] = *reinterpret_cast<uint32_t*>(&h3);
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        const uint4 bv = bcur[nt][j >> 1];
+                        const uint32_t b0 = (j & 1) ? bv.z : bv.x;
+                        const uint32_t b1 = (j & 1) ? bv.w : bv.y;
+                        if (j == 0)
+                            mma_16816_f16(accg[nt], a, b0, b1, zero4);
+                        else
+                            mma_16816_f16(accg[nt], a, b0, b1, accg[nt]);
+                    }
+                }
+            }
+            const float s_lo = __low2float(sc), s_hi = __high2float(sc);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                acc[tt][nt][0] = fmaf(s_lo, accg[nt][0], acc[tt][nt][0]);
+                acc[tt][nt][1] = fmaf(s_lo, accg[nt][1], acc[tt][nt][1]);
+                acc[tt][nt][2] = fmaf(s_hi, accg[nt][2], acc[tt][nt][2]);
+                acc[tt][nt][3] = fmaf(s_hi, accg[nt][3], acc[tt][nt][3]);
+            }
+        }
+        __syncwarp();   // all lanes finished reading stage s
+        if (lane == 0 && i + kW4Stages < ng) {
+            mbar_expect_tx(&bars[s], kW4BlockBytes);
+            bulk_g2s(ring + s * kW4BlockBytes, gsrc + (size_t)(i + kW4Stages) * kW4BlockBytes, kW4BlockBytes,
+                     &bars[s]);
+        }
+    }
+
+    // ---- split-k reduction across the 8 warps through this warp's (now idle) ring ----
+    float* red = reinterpret_cast<float*>(ring);   // [tok (NT*8)][32 rows]
+#pragma unroll
+    for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const int tok = nt * 8 + 2 * t;
+            const int row = tt * 16 + g;
+            red[tok * 32 + row] = acc[tt][nt][0];
+            red[(tok + 1) * 32 + row] = acc[tt][nt][1];
+            red[tok * 32 + row + 8] = acc[tt][nt][2];
+            red[(tok + 1) * 32 + row + 8] = acc[tt][nt][3];
+        }
+    __syncthreads();
+
+    const int n0 = st * 32;
+    auto sum_red = [&](int idx) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < kW4Warps; ++w)
+            v += reinterpret_cast<const float*>(smem + w * (kW4Stages * kW4BlockBytes))[idx];
+        return v;
+    };
+    if (epi == ZL_EPI_SWIGLU) {
+        const int n_out = N / 2;
+        for (int e = threadIdx.x; e < mc * 16; e += blockDim.x) {
+            const int tok = e >> 4, oc = e & 15;
+            const int rg = (oc >> 3) * 16 + (oc & 7);   // gate row within the super tile; up = rg + 8
+            float gate = sum_red(tok * 32 + rg);
+            float up = sum_red(tok * 32 + rg + 8);
+            if (bias) {
+                gate += __half2float(bias[n0 + rg]);
+                up += __half2float(bias[n0 + rg + 8]);
+            }
+            // reference order: both GEMV outputs are rounded to fp16, then silu*mul in fp32
+            // (feedforward.cpp:126-133, activation_kernel.cu:71-80)
+            const float gr = __half2float(__float2half_rn(gate));
+            const float ur = __half2float(__float2half_rn(up));
+            y[(size_t)tok * n_out + st * 16 + oc] = __float2half_rn(silu_f(gr) * ur);
+        }
+    } else {
+        for (int e = threadIdx.x; e < mc * 32; e += blockDim.x) {
+            const int tok = e >> 5, row = e & 31;
+            float v = sum_red(tok * 32 + row);
+            if (bias) v += __half2float(bias[n0 + row]);
+            __half h = __float2half_rn(v);
+            if (epi == ZL_EPI_RESIDUAL)
+                h = __float2half_rn(__half2float(h) + __half2float(residual[(size_t)tok * N + n0 + row]));
+            y[(size_t)tok * N + n0 + row] = h;
+        }
+    }
+}
+
+template <int NT>
+static cudaError_t launch_w4(const __half* x, int ldx, const uint8_t* packed, const __half* bias,
+                             const __half* residual, __half* y, int mc, int N, int K, int epi, bool pdl,
+                             cudaStream_t stream) {
+    static bool attr_set = false;   // idempotent; a race only repeats the call
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_w4a16_mma<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kW4SmemBytes);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    return launch(k_w4a16_mma<NT>, dim3(N / 32), dim3(kW4Warps * 32), kW4SmemBytes, stream, pdl, x, ldx, packed,
+                  bias, residual, y, mc, N, K, epi);
+}
+
+}  // namespace zl
+
+using namespace zl;
+
+extern "C" int zl_w4a16_gemm(const void* x, int ldx, const void* packed, const void* bias, const void* residual,
+                             void* y, int M, int N, int K, int group_size, int epilogue, int pdl,
+                             zl_stream_t stream) {
+    ZL_CHECK_ARG(x && packed && y && M > 0 && N > 0 && K > 0);
+    ZL_CHECK_SUPPORTED(group_size == kW4GroupK);
+    ZL_CHECK_SUPPORTED(N % 32 == 0 && K % kW4GroupK == 0);
+    ZL_CHECK_ARG(ldx >= K && ldx % 8 == 0);
+    ZL_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(packed) & 15) == 0);
+    ZL_CHECK_ARG(epilogue == ZL_EPI_NONE || epilogue == ZL_EPI_SWIGLU || epilogue == ZL_EPI_RESIDUAL);
+    ZL_CHECK_ARG(epilogue != ZL_EPI_RESIDUAL || residual != nullptr);
+    const int n_out = epilogue == ZL_EPI_SWIGLU ? N / 2 : N;
+    const __half* xp = static_cast<const __half*>(x);
+    const __half* rp = static_cast<const __half*>(residual);
+    __half* yp = static_cast<__half*>(y);
+    for (int m0 = 0; m0 < M; m0 += 32) {
+        const int mc = (M - m0) < 32 ? (M - m0) : 32;
+        const __half* xc = xp + (size_t)m0 * ldx;
+        const __half* rc = rp ? rp + (size_t)m0 * N : nullptr;
+        __half* yc = yp + (size_t)m0 * n_out;
+        cudaError_t e;
+        const bool use_pdl = pdl != 0 && m0 == 0;
+        if (mc <= 8)
+            e = launch_w4<1>(xc, ldx, (const uint8_t*)packed, (const __half*)bias, rc, yc, mc, N, K, epilogue,
+                             use_pdl, stream);
+        else if (mc <= 16)
+            e = launch_w4<2>(xc, ldx, (const uint8_t*)packed, (const __half*)bias, rc, yc, mc, N, K, epilogue,
+                             use_pdl, stream);
+        else
+            e = launch_w4<4>(xc, ldx, (const uint8_t*)packed, (const __half*)bias, rc, yc, mc, N, K, epilogue,
+                             use_pdl, stream);
+        ZL_CHECK_CUDA(e);
+    }
+    return ZL_OK;
+}
