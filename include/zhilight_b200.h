@@ -213,10 +213,16 @@ int zl_llama_decode(zl_llama_t* m, const int32_t* tokens_host, const int32_t* po
  * tokens back and advances positions on the device; no host sync. */
 int zl_llama_set_state(zl_llama_t* m, const int32_t* tokens_host, const int32_t* positions_host, int B);
 int zl_llama_step_device(zl_llama_t* m, int B);
+/* read back the device-resident (token, position) state; synchronous. */
+int zl_llama_get_state(zl_llama_t* m, int32_t* tokens_host, int32_t* positions_host, int B);
 int zl_llama_sync(zl_llama_t* m);
 zl_stream_t zl_llama_stream(zl_llama_t* m);
 /* bytes the step must read from HBM per rank (weights + lm_head + norms), kernel launches per step. */
 int zl_llama_stats(zl_llama_t* m, int B, double* weight_bytes, int* kernels_per_step);
+/* Roofline probe for the dominant kernel: enqueue only the W4A16 (or dense) GEMMs of one decode step
+ * (every layer's own weights, same PDL chain) `iters` times between CUDA events on the driver's stream.
+ * Returns total milliseconds, the number of GEMM launches and their algorithmic bytes. */
+int zl_llama_bench_gemms(zl_llama_t* m, int B, int iters, float* ms, int* launches, double* bytes);
 
 #ifdef __cplusplus
 }

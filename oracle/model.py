@@ -12,6 +12,20 @@ from . import gptq, ops
 F32 = np.float32
 
 
+def _f32(a, dtype):
+    """Checkpoint tensor -> fp32 values.  bf16 tensors travel as uint16 bit patterns (numpy has no bf16)."""
+    a = np.asarray(a)
+    if a.dtype == np.uint16:
+        return (a.astype(np.uint32) << 16).view(np.float32)
+    return a.astype(F32)
+
+
+def to_bf16_bits(x):
+    u = np.asarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u >> 16) & 1) + 0x7FFF
+    return ((u + r) >> 16).astype(np.uint16)
+
+
 class OracleLlama:
     def __init__(self, cfg, state_dict, quant_type=0, group_size=128, sym=False, dtype="f16"):
         """cfg: dict with num_layers, dim_model, num_heads, num_kv_heads, dim_head, dim_ff, vocab_size, eps,
@@ -39,7 +53,7 @@ class OracleLlama:
                                             None, self.group_size, is_awq=True)
             w = gptq.dequant_k_major_f32(qw, qz, sc, False)
         else:
-            w = ops._t(np.asarray(sd[prefix + ".weight"], dtype=F32), self.dtype)
+            w = _f32(sd[prefix + ".weight"], self.dtype)
         self.w[prefix] = w
         return w
 
@@ -47,7 +61,7 @@ class OracleLlama:
         y = np.asarray(x, F32) @ self._weight(prefix).T
         b = self.sd.get(prefix + ".bias")
         if b is not None:
-            y = y + np.asarray(b, F32)[None, :]
+            y = y + _f32(b, self.dtype)[None, :]
         return ops._t(y, self.dtype)
 
     def decode(self, tokens, positions, tasks=None):
@@ -56,13 +70,13 @@ class OracleLlama:
         b = len(tokens)
         tasks = list(range(b)) if tasks is None else tasks
         d, hq, hkv = c["dim_head"], c["num_heads"], c["num_kv_heads"]
-        emb = ops._t(np.asarray(self.sd["token_embedding.weight"], F32), T)
+        emb = _f32(self.sd["token_embedding.weight"], T)
         h = emb[np.asarray(tokens)]
         cos, sin = ops.rope_cos_sin(np.asarray(positions), d, c["rope_theta"], c.get("rope_llama3"))
         scale = F32(1.0 / np.sqrt(d))
         for l in range(c["num_layers"]):
             p = "layers.%d." % l
-            xn = ops.rmsnorm(h, self.sd[p + "ln_attn.weight"], c["eps"], 1.0, T)
+            xn = ops.rmsnorm(h, _f32(self.sd[p + "ln_attn.weight"], T), c["eps"], 1.0, T)
             q = self._linear(xn, p + "attn.project_q")
             k = self._linear(xn, p + "attn.project_k")
             v = self._linear(xn, p + "attn.project_v")
@@ -87,26 +101,29 @@ class OracleLlama:
                 ao[i] = o.reshape(-1)
             o = self._linear(ao, p + "attn.attn_out")
             h = ops.residual_add(h, o, T)
-            xn = ops.rmsnorm(h, self.sd[p + "ln_ff.weight"], c["eps"], 1.0, T)
+            xn = ops.rmsnorm(h, _f32(self.sd[p + "ln_ff.weight"], T), c["eps"], 1.0, T)
             g = self._linear(xn, p + "ff.w_in")
             u = self._linear(xn, p + "ff.w_gated")
             act = ops.silu_mul(g, u, T)
             dn = self._linear(act, p + "ff.w_out")
             h = ops.residual_add(h, dn, T)
-        xn = ops.rmsnorm(h, self.sd["output_layernorm.weight"], c["eps"], 1.0, T)
+        xn = ops.rmsnorm(h, _f32(self.sd["output_layernorm.weight"], T), c["eps"], 1.0, T)
         lm = self.sd.get("lm_head.weight", self.sd["token_embedding.weight"])
-        return np.asarray(xn, F32) @ ops._t(np.asarray(lm, F32), T).T
+        return np.asarray(xn, F32) @ _f32(lm, T).T
 
 
-def make_state_dict(cfg, quant_type=0, group_size=128, sym=False, seed=0, tied=False):
+def make_state_dict(cfg, quant_type=0, group_size=128, sym=False, seed=0, tied=False, dtype="f16"):
     """Random checkpoint with ZhiLight names (zhilight/loader.py:250-358)."""
     rng = np.random.default_rng(seed)
     c = cfg
     d_model, d = c["dim_model"], c["dim_head"]
     sd = {}
 
+    def cast(a):
+        return to_bf16_bits(a) if dtype == "bf16" else np.asarray(a).astype(np.float16)
+
     def dense(n, k):
-        return (rng.standard_normal((n, k)) * 0.05).astype(np.float16)
+        return cast(rng.standard_normal((n, k)) * 0.05)
 
     def linear(prefix, k, n, s):
         if quant_type == 5:
@@ -123,8 +140,8 @@ def make_state_dict(cfg, quant_type=0, group_size=128, sym=False, seed=0, tied=F
     s = seed * 1000
     for l in range(c["num_layers"]):
         p = "layers.%d." % l
-        sd[p + "ln_attn.weight"] = (1.0 + 0.1 * rng.standard_normal(d_model)).astype(np.float16)
-        sd[p + "ln_ff.weight"] = (1.0 + 0.1 * rng.standard_normal(d_model)).astype(np.float16)
+        sd[p + "ln_attn.weight"] = cast(1.0 + 0.1 * rng.standard_normal(d_model))
+        sd[p + "ln_ff.weight"] = cast(1.0 + 0.1 * rng.standard_normal(d_model))
         linear(p + "attn.project_q", d_model, c["num_heads"] * d, s + 1)
         linear(p + "attn.project_k", d_model, c["num_kv_heads"] * d, s + 2)
         linear(p + "attn.project_v", d_model, c["num_kv_heads"] * d, s + 3)
@@ -134,7 +151,7 @@ def make_state_dict(cfg, quant_type=0, group_size=128, sym=False, seed=0, tied=F
         linear(p + "ff.w_out", c["dim_ff"], d_model, s + 7)
         s += 10
     sd["token_embedding.weight"] = dense(c["vocab_size"], d_model)
-    sd["output_layernorm.weight"] = (1.0 + 0.1 * rng.standard_normal(d_model)).astype(np.float16)
+    sd["output_layernorm.weight"] = cast(1.0 + 0.1 * rng.standard_normal(d_model))
     if not tied:
         sd["lm_head.weight"] = dense(c["vocab_size"], d_model)
     return sd

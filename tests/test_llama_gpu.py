@@ -1,0 +1,98 @@
+"""GPU parity: the whole decode step (driver + every kernel) against the CPU oracle model on small
+synthetic checkpoints -- the round trip a user of zhilight.LLaMA / DynamicBatchGenerator sees:
+state_dict in (HF-GPTQ layout), (token, position) per task in, logits / greedy tokens out."""
+import numpy as np
+import pytest
+
+from oracle import model as omodel
+from tests.helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TINY = dict(num_layers=2, dim_model=256, num_heads=4, num_kv_heads=2, dim_head=64, dim_ff=512, vocab_size=512,
+            eps=1e-5, rope_theta=10000.0, rope_llama3=None)
+TINY128 = dict(num_layers=2, dim_model=512, num_heads=4, num_kv_heads=1, dim_head=128, dim_ff=640, vocab_size=1000,
+               eps=1e-5, rope_theta=500000.0, rope_llama3=dict(factor=8.0, low=1.0, high=4.0, orig=8192.0))
+
+
+def _run(cfg, quant, dtype, sym=False, use_pdl=True, use_graph=True, steps=6, tied=False, seed=0):
+    from zhilight_b200.llama import LlamaDecoder
+    sd = omodel.make_state_dict(cfg, quant, 128, sym, seed=seed, tied=tied, dtype=dtype)
+    dec = LlamaDecoder(quant_type=quant, group_size=128, sym=sym, dtype=dtype, max_batch=3, max_seq=64,
+                       use_pdl=use_pdl, use_graph=use_graph, **cfg)
+    dec.load_state_dict(sd)
+    orc = omodel.OracleLlama(cfg, sd, quant, 128, sym, dtype)
+    rng = np.random.default_rng(seed)
+    # three tasks at different positions (ragged batch, like the dynamic batcher produces)
+    pos = np.array([0, 0, 0], dtype=np.int32)
+    tok = rng.integers(0, cfg["vocab_size"], size=3).astype(np.int32)
+    outs = []
+    for s in range(steps):
+        b = 3 if s % 3 != 2 else 2                      # batch size changes between steps
+        nxt, logits = dec.decode(tok[:b], pos[:b], want_logits=True)
+        ref = orc.decode(tok[:b], pos[:b], tasks=list(range(b)))
+        outs.append((nxt.copy(), logits.copy(), ref))
+        tok[:b] = rng.integers(0, cfg["vocab_size"], size=b)      # teacher forcing with random tokens
+        pos[:b] += 1
+    dec.close()
+    return outs
+
+
+@pytest.mark.parametrize("cfg", [TINY, TINY128], ids=["d64", "d128-llama3rope"])
+@pytest.mark.parametrize("sym", [False, True])
+def test_gptq_decode_matches_oracle(lib, cuda, cfg, sym):
+    for nxt, logits, ref in _run(cfg, 5, "f16", sym=sym):
+        # north_star: logits within 1e-3 rel for fp16 -- measured as relative L2 over the vocabulary
+        assert rel_l2(logits, ref) <= 2e-3
+        for b in range(len(nxt)):
+            order = np.argsort(ref[b])
+            if ref[b][order[-1]] - ref[b][order[-2]] > 1e-2:
+                assert nxt[b] == order[-1]
+
+
+def test_awq_decode_matches_oracle(lib, cuda):
+    for nxt, logits, ref in _run(TINY, 6, "f16"):
+        assert rel_l2(logits, ref) <= 2e-3
+
+
+@pytest.mark.parametrize("dtype,tol", [("f16", 2e-3), ("bf16", 2e-2)])
+def test_dense_decode_matches_oracle(lib, cuda, dtype, tol):
+    """BASELINE config 2 path (Llama-3.2-1B bf16: no quant, tied lm_head, d=64 attention)."""
+    for nxt, logits, ref in _run(TINY, 0, dtype, tied=True):
+        assert rel_l2(logits, ref) <= tol
+
+
+def test_graph_and_pdl_do_not_change_results(lib, cuda):
+    a = _run(TINY, 5, "f16", use_pdl=False, use_graph=False)
+    b = _run(TINY, 5, "f16", use_pdl=True, use_graph=False)
+    c = _run(TINY, 5, "f16", use_pdl=True, use_graph=True)
+    for (na, la, _), (nb, lb, _), (nc, lc, _) in zip(a, b, c):
+        np.testing.assert_array_equal(la, lb)
+        np.testing.assert_array_equal(la, lc)
+        np.testing.assert_array_equal(na, nc)
+
+
+def test_device_resident_stepping_matches_host_stepping(lib, cuda):
+    """bench.py times the device-resident loop (`value`) and the host-fed loop (`e2e`); both must decode
+    the same greedy sequence."""
+    from zhilight_b200.llama import LlamaDecoder
+    sd = omodel.make_state_dict(TINY, 5, 128, False, seed=3)
+    finals = []
+    for mode in ("host", "device"):
+        dec = LlamaDecoder(quant_type=5, max_batch=2, max_seq=64, **TINY)
+        dec.load_state_dict(sd)
+        tok = np.array([7, 400], dtype=np.int32)
+        pos = np.array([0, 0], dtype=np.int32)
+        if mode == "host":
+            for _ in range(8):
+                tok = dec.decode(tok, pos)
+                pos = pos + 1
+        else:
+            dec.set_state(tok, pos)
+            for _ in range(8):
+                dec.step_device(2)
+            tok, pos = dec.get_state(2)
+        finals.append((tok.copy(), pos.copy()))
+        dec.close()
+    np.testing.assert_array_equal(finals[0][0], finals[1][0])
+    np.testing.assert_array_equal(finals[0][1], finals[1][1])

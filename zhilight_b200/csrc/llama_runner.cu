@@ -636,6 +636,74 @@ extern "C" int zl_llama_decode(zl_llama_t* m, const int32_t* tokens_host, const 
     return ZL_OK;
 }
 
+extern "C" int zl_llama_get_state(zl_llama_t* m, int32_t* tokens_host, int32_t* positions_host, int B) {
+    ZL_CHECK_ARG(m && tokens_host && positions_host && B > 0 && B <= m->cfg.max_batch);
+    ZL_CHECK_CUDA(cudaMemcpyAsync(m->h_stage, m->d_tokens, B * 4, cudaMemcpyDeviceToHost, m->stream));
+    ZL_CHECK_CUDA(cudaMemcpyAsync(m->h_stage + B, m->d_pos, B * 4, cudaMemcpyDeviceToHost, m->stream));
+    ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+    for (int i = 0; i < B; ++i) {
+        tokens_host[i] = m->h_stage[i];
+        positions_host[i] = m->h_stage[B + i];
+    }
+    return ZL_OK;
+}
+
+extern "C" int zl_llama_bench_gemms(zl_llama_t* m, int B, int iters, float* ms, int* launches, double* bytes) {
+    ZL_CHECK_ARG(m && B > 0 && B <= m->cfg.max_batch && iters > 0 && ms);
+    const auto& c = m->cfg;
+    const int D = c.dim_model, d = c.dim_head, dt = c.dtype, pdl = c.use_pdl;
+    const bool w4 = c.quant_type == 5 || c.quant_type == 6;
+    cudaStream_t st = m->stream;
+    cudaEvent_t e0, e1;
+    ZL_CHECK_CUDA(cudaEventCreate(&e0));
+    ZL_CHECK_CUDA(cudaEventCreate(&e1));
+    int n_launch = 0;
+    double nbytes = 0;
+    for (int it = -1; it < iters; ++it) {   // it == -1: warm-up pass
+        if (it == 0) ZL_CHECK_CUDA(cudaEventRecord(e0, st));
+        for (int l = 0; l < c.num_layers; ++l) {
+            Layer& L = m->layers[l];
+            if (w4) {
+                RCHECK(zl_w4a16_gemm(m->xn, D, L.q_qkv.packed, L.q_qkv.bias, nullptr, m->qkv, B, L.q_qkv.N, D,
+                                     c.group_size, ZL_EPI_NONE, pdl, st));
+                RCHECK(zl_w4a16_gemm(m->ao, m->hq * d, L.q_o.packed, L.q_o.bias, m->pend, m->pend, B, D, m->hq * d,
+                                     c.group_size, ZL_EPI_RESIDUAL, pdl, st));
+                RCHECK(zl_w4a16_gemm(m->xn, D, L.q_gu.packed, nullptr, nullptr, m->act, B, L.q_gu.N, D,
+                                     c.group_size, ZL_EPI_SWIGLU, pdl, st));
+                RCHECK(zl_w4a16_gemm(m->act, m->ff, L.q_down.packed, L.q_down.bias, m->pend, m->pend, B, D, m->ff,
+                                     c.group_size, ZL_EPI_RESIDUAL, pdl, st));
+                if (it == 0) {
+                    nbytes += (double)zl_w4_packed_bytes(L.q_qkv.N, D, c.group_size) +
+                              (double)zl_w4_packed_bytes(D, m->hq * d, c.group_size) +
+                              (double)zl_w4_packed_bytes(L.q_gu.N, D, c.group_size) +
+                              (double)zl_w4_packed_bytes(D, m->ff, c.group_size);
+                    // activations in/out (fp16)
+                    nbytes += 2.0 * B * (D + L.q_qkv.N + m->hq * d + 2 * D + D + m->ff + m->ff + 2 * D);
+                }
+            } else {
+                RCHECK(zl_dense_gemm_skinny(m->xn, D, L.d_qkv.w, L.d_qkv.bias, m->qkv, B, L.d_qkv.N, D, dt, dt, pdl, st));
+                RCHECK(zl_dense_gemm_skinny(m->ao, m->hq * d, L.d_o.w, L.d_o.bias, m->pend, B, D, m->hq * d, dt, dt,
+                                            pdl, st));
+                RCHECK(zl_dense_gemm_skinny(m->xn, D, L.d_gu.w, L.d_gu.bias, m->gu, B, 2 * m->ff, D, dt, dt, pdl, st));
+                RCHECK(zl_dense_gemm_skinny(m->act, m->ff, L.d_down.w, L.d_down.bias, m->pend, B, D, m->ff, dt, dt,
+                                            pdl, st));
+                if (it == 0)
+                    nbytes += 2.0 * ((double)L.d_qkv.N * D + (double)D * m->hq * d + 2.0 * m->ff * D + (double)D * m->ff) +
+                              2.0 * B * (D + L.d_qkv.N + m->hq * d + D + D + 2 * m->ff + m->ff + D);
+            }
+            if (it == 0) n_launch += 4;
+        }
+    }
+    ZL_CHECK_CUDA(cudaEventRecord(e1, st));
+    ZL_CHECK_CUDA(cudaEventSynchronize(e1));
+    ZL_CHECK_CUDA(cudaEventElapsedTime(ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (launches) *launches = n_launch;
+    if (bytes) *bytes = nbytes;
+    return ZL_OK;
+}
+
 extern "C" int zl_llama_sync(zl_llama_t* m) {
     ZL_CHECK_ARG(m);
     ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));

@@ -85,6 +85,13 @@ class LlamaDecoder:
         _lib.check(self.lib.zl_llama_set_state(self.h, t.ctypes.data_as(ctypes.c_void_p),
                                                p.ctypes.data_as(ctypes.c_void_p), t.size))
 
+    def get_state(self, b):
+        t = np.empty(b, dtype=np.int32)
+        p = np.empty(b, dtype=np.int32)
+        _lib.check(self.lib.zl_llama_get_state(self.h, t.ctypes.data_as(ctypes.c_void_p),
+                                               p.ctypes.data_as(ctypes.c_void_p), b))
+        return t, p
+
     def step_device(self, b):
         _lib.check(self.lib.zl_llama_step_device(self.h, b))
 
@@ -93,6 +100,14 @@ class LlamaDecoder:
 
     def stream(self):
         return self.lib.zl_llama_stream(self.h)
+
+    def bench_gemms(self, b=1, iters=5):
+        """-> (ms for `iters` passes, GEMM launches per pass, algorithmic bytes per pass)."""
+        ms = ctypes.c_float()
+        n = ctypes.c_int()
+        by = ctypes.c_double()
+        _lib.check(self.lib.zl_llama_bench_gemms(self.h, b, iters, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(by)))
+        return ms.value, n.value, by.value
 
     def stats(self, b=1):
         wb = ctypes.c_double()
