@@ -49,6 +49,9 @@ const char* zl_last_error(void);
 int zl_version(void);
 /* number of kernel launches issued by this library on the calling thread since the last reset */
 long long zl_launch_count(int reset);
+/* one-time per-device kernel attribute setup (opt-in shared memory); called by zl_llama_create and lazily
+ * by the ops; must not first happen inside a stream capture. */
+int zl_prepare(void);
 
 /* ------------------------------------------------------------------------------------------ *
  * Load-time integer layout transforms (bit-exact with the reference)

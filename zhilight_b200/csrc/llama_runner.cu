@@ -464,6 +464,7 @@ extern "C" int zl_llama_create(const zl_llama_config_t* cfg, zl_llama_t** out) {
     ZL_CHECK_SUPPORTED(cfg->tp_size >= 1 && cfg->tp_rank >= 0 && cfg->tp_rank < cfg->tp_size);
     ZL_CHECK_SUPPORTED(cfg->tp_size == 1);   // TP goes through zl_comm; not wired in the driver yet
     ZL_CHECK_SUPPORTED(cfg->quant_type == 0 || cfg->group_size == zl::kW4GroupK);
+    RCHECK(zl_prepare());
     zl_llama* m = new zl_llama();
     m->cfg = *cfg;
     m->hq = cfg->num_heads / cfg->tp_size;

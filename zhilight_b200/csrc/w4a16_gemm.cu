@@ -239,6 +239,14 @@ static cudaError_t launch_w4(const __half* x, int ldx, const uint8_t* packed, co
 
 using namespace zl;
 
+extern "C" int zl_prepare(void) {
+    // opt-in shared memory sizes must be configured outside of stream capture
+    ZL_CHECK_CUDA(cudaFuncSetAttribute(k_w4a16_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kW4SmemBytes));
+    ZL_CHECK_CUDA(cudaFuncSetAttribute(k_w4a16_mma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kW4SmemBytes));
+    ZL_CHECK_CUDA(cudaFuncSetAttribute(k_w4a16_mma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kW4SmemBytes));
+    return ZL_OK;
+}
+
 extern "C" int zl_w4a16_gemm(const void* x, int ldx, const void* packed, const void* bias, const void* residual,
                              void* y, int M, int N, int K, int group_size, int epilogue, int pdl,
                              zl_stream_t stream) {
