@@ -1,0 +1,91 @@
+"""Seeded inputs of the golden cases (TEST INFRASTRUCTURE).
+
+`oracle/gen_ref_golden.py` feeds them to the REFERENCE's own kernels (oracle/_ref/libzl_ref.so, on the B200 box)
+and stores the outputs in tests/golden/ref_<case>.npz; `oracle/check_golden.py` regenerates the same inputs on
+the CPU, runs the oracle and compares -- that is what pins the oracle to the reference.
+"""
+import numpy as np
+
+from . import gptq, ops
+
+
+def _rng(seed):
+    return np.random.default_rng(seed)
+
+
+def case_gptq_layout():
+    k, n, g = 256, 64, 128
+    qw, qz, sc, gi = gptq.make_gptq_checkpoint(k, n, g, False, seed=101)
+    return dict(qweight=qw, qzeros=qz, scales=sc, K=k, N=n, G=k // g)
+
+
+def case_awq_layout():
+    k, n, g = 256, 64, 128
+    r = _rng(102)
+    qw = r.integers(0, 2 ** 32, size=(k, n // 8), dtype=np.uint64).astype(np.uint32).view(np.int32)
+    qz = r.integers(0, 2 ** 32, size=(k // g, n // 8), dtype=np.uint64).astype(np.uint32).view(np.int32)
+    sc = (0.005 + 0.015 * r.random((k // g, n))).astype(np.float16)
+    return dict(qweight=qw, qzeros=qz, scales=sc, K=k, N=n, G=k // g)
+
+
+def case_gemv(sym):
+    k, n, g = 1024, 256, 128
+    qw, qz, sc, gi = gptq.make_gptq_checkpoint(k, n, g, sym, seed=103 + int(sym))
+    qw_km, qz_km, sc_km, _ = gptq.to_k_major(qw, qz, sc, gi, g)
+    r = _rng(105)
+    xs = {m: r.standard_normal((m, k)).astype(np.float16) for m in (1, 3, 16, 33)}
+    bias = r.standard_normal(n).astype(np.float16)
+    return dict(qw_km=qw_km.view(np.int32), qz_km=qz_km, sc_km=sc_km, xs=xs, bias=bias, K=k, N=n, G=k // g, sym=sym)
+
+
+def case_gate_in():
+    k, f, g = 512, 128, 128
+    a = gptq.make_gptq_checkpoint(k, f, g, False, seed=106)
+    b = gptq.make_gptq_checkpoint(k, f, g, False, seed=107)
+    ka = gptq.to_k_major(a[0], a[1], a[2], a[3], g)
+    kb = gptq.to_k_major(b[0], b[1], b[2], b[3], g)
+    r = _rng(108)
+    xs = {m: r.standard_normal((m, k)).astype(np.float16) for m in (1, 2)}
+    return dict(gate=ka[:3], up=kb[:3], xs=xs, K=k, F=f, G=k // g)
+
+
+def case_norm():
+    r = _rng(109)
+    t, d = 5, 1024
+    return dict(a=r.standard_normal((t, d)).astype(np.float16), b=r.standard_normal((t, d)).astype(np.float16),
+                w=(1 + 0.1 * r.standard_normal(d)).astype(np.float16), eps=1e-5, T=t, D=d)
+
+
+def case_rope():
+    r = _rng(110)
+    t, hq, hkv, d = 6, 8, 2, 128
+    pos = np.array([0, 1, 5, 100, 1000, 4000], dtype=np.int32)
+    cos, sin = ops.rope_cos_sin(pos, d, 500000.0, dict(factor=8.0, low=1.0, high=4.0, orig=8192.0))
+    return dict(qkv=r.standard_normal((t, (hq + 2 * hkv) * d)).astype(np.float16), cos=cos, sin=sin, T=t, hq=hq,
+                hkv=hkv, d=d)
+
+
+def case_attention(long):
+    r = _rng(111 + int(long))
+    hq, hkv, d = 8, 2, 128
+    lens = [1600, 600] if long else [96, 33, 128]
+    b = len(lens)
+    q = r.standard_normal((b, 1, hq, d)).astype(np.float16)
+    ks = [r.standard_normal((lb, hkv, d)).astype(np.float16) for lb in lens]
+    vs = [r.standard_normal((lb, hkv, d)).astype(np.float16) for lb in lens]
+    masks = []
+    for lb in lens:
+        m = np.ones((1, lb), np.int8)
+        m[0, lb - 2:] = 0
+        m[0, r.permutation(lb - 2)[: lb // 9]] = 0
+        masks.append(m)
+    return dict(q=q, ks=ks, vs=vs, masks=masks, lens=np.array(lens, np.int32), hq=hq, hkv=hkv, d=d,
+                scale=float(1.0 / np.sqrt(d)))
+
+
+def case_int8():
+    r = _rng(113)
+    m, k, ws = 4, 512, 4
+    x = r.standard_normal((m, k)).astype(np.float16)
+    parts = [r.standard_normal((8, 256)).astype(np.float16) for _ in range(ws)]
+    return dict(x=x, parts=parts, WS=ws)
