@@ -191,6 +191,7 @@ def main():
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fuse", type=int, default=2, help="0: one kernel per reference op; 1: +RMSNorm fused; 2: +qkv RoPE/KV epilogue")
     args = ap.parse_args()
 
     cfg = model_cfg(args.model)
@@ -222,7 +223,7 @@ def main():
     W = max(args.warmup, 3)
     max_seq = args.prompt + 2 * W + 2 * args.steps + 16
     dec = LlamaDecoder(quant_type=0 if dense else 5, group_size=128, sym=True, dtype="bf16" if dense else "f16",
-                       max_batch=args.batch, max_seq=max_seq, use_pdl=not args.no_pdl, use_graph=not args.no_graph,
+                       max_batch=args.batch, max_seq=max_seq, use_pdl=not args.no_pdl, use_graph=not args.no_graph, fuse=args.fuse,
                        **cfg)
     dec.init_synthetic(seed=1 + rank)
     B = args.batch
@@ -313,7 +314,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload, "parallelism": "single GPU" if world == 1 else "dp%d replicas" % world,
                    "l2": "weights per step (%.2f GB) exceed L2 (126 MB); no explicit flush" % (weight_bytes / 1e9),
-                   "pdl": not args.no_pdl, "cuda_graph": not args.no_graph},
+                   "pdl": not args.no_pdl, "cuda_graph": not args.no_graph, "fuse": args.fuse},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 4 * B,
                 "ms_per_step": ms_e2e / args.steps},

@@ -42,7 +42,8 @@ enum { ZL_F16 = 0, ZL_BF16 = 1, ZL_F32 = 2 };
 enum {
     ZL_EPI_NONE = 0,     /* y = acc (+bias)                                                     */
     ZL_EPI_SWIGLU = 1,   /* packed rows interleave gate/up; y[:, n] = silu(T(gate)) * T(up)      */
-    ZL_EPI_RESIDUAL = 2  /* y = T(T(acc (+bias)) + residual)   (block_kernel.cu:7-17)           */
+    ZL_EPI_RESIDUAL = 2, /* y = T(T(acc (+bias)) + residual)   (block_kernel.cu:7-17)           */
+    ZL_EPI_QKV_ROPE = 3  /* fused qkv: split + RoPE(q,k) + KV append (zl_w4a16_gemm_fused only)    */
 };
 
 const char* zl_last_error(void);
@@ -98,6 +99,27 @@ int zl_w4_unpack(const void* packed, uint32_t* qweight_km, uint8_t* qzeros_km, v
  * Any M >= 1 (weights are re-streamed per 32-token chunk).  pdl != 0 -> programmatic dependent launch. */
 int zl_w4a16_gemm(const void* x, int ldx, const void* packed, const void* bias, const void* residual,
                   void* y, int M, int N, int K, int group_size, int epilogue, int pdl, zl_stream_t stream);
+
+/* The same GEMM with the neighbouring operators of the decode layer folded in:
+ *   ln_weight != NULL : nn::LayerNorm (rms, layernorm.cu:9-42) of x is fused into the prologue:
+ *                       y = rsqrt(mean(x^2)+eps) * (W . (x*ln_weight)) (+bias);
+ *   epilogue ZL_EPI_QKV_ROPE: W is the fused qkv weight packed with zl_qkv_rope_row_map; the epilogue applies
+ *                       rope_qk_cache (rotary_embedding_fuse_cache.cu:23-63) and copy_to_rag_buffer2
+ *                       (ragged_buffer_kernel.cu:194-222, BSHD) and writes q (M, num_heads*dim_head).
+ * bias is indexed by PACKED row. */
+typedef struct zl_w4_fused_args {
+    const void* x; int ldx; const void* packed; const void* bias; const void* residual; void* y;
+    int M, N, K, group_size, epilogue, pdl;
+    const void* ln_weight; float eps;
+    const float* cos; const float* sin; void* q_out;
+    const int32_t* token_batch; const int32_t* placement; void* const* k_addrs; void* const* v_addrs;
+    int num_heads, num_kv_heads, dim_head;
+} zl_w4_fused_args_t;
+int zl_w4a16_gemm_fused(const zl_w4_fused_args_t* args, zl_stream_t stream);
+/* row_map (n_heads_total*dim_head) for zl_w4_pack so that RoPE partners (c, c+d/2) share an MMA tile. */
+int zl_qkv_rope_row_map(int32_t* row_map, int n_heads_total, int dim_head, zl_stream_t stream);
+/* dst[i] = src[map[i]] for 16-bit elements (bias permutation to packed-row order). */
+int zl_gather_rows_16(const void* src, const int32_t* map, void* dst, int n, zl_stream_t stream);
 
 /* functions::Gemm / NormalLinear for skinny M (lm_head, bf16 models; src/nn/linear/linear.cpp:150-430,
  * src/nn/embedding/embedding.cu:353-392): y(M,N) = x(M,K) @ W(N,K)^T (+bias), dtype f16/bf16,
@@ -195,6 +217,7 @@ typedef struct zl_llama_config {
     int max_batch, max_seq;
     int tp_rank, tp_size;
     int use_pdl, use_graph;
+    int fuse; /* 0: one kernel per reference operator; 1: RMSNorm folded into the W4 GEMMs; 2: + qkv RoPE/KV-append epilogue */
 } zl_llama_config_t;
 
 int zl_llama_create(const zl_llama_config_t* cfg, zl_llama_t** out);

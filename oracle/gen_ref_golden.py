@@ -252,3 +252,5 @@ def main(out_dir):
 
 if __name__ == "__main__":
     main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "..", "gpurun_out", "golden"))
+    sys.stdout.flush()
+    os._exit(0)      # bmengine statics are torn down after the CUDA driver at interpreter exit

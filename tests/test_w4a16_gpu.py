@@ -132,3 +132,72 @@ def test_rejects_bf16_like_reference(lib, cuda):
     w, packed, _ = _setup(cuda, 128, 32, False, 11)
     with pytest.raises(ZLError):
         ops.w4a16_gemm(torch.zeros(1, 128, dtype=torch.bfloat16, device=cuda), packed, 32, 128)
+
+
+@pytest.mark.parametrize("m", [1, 5, 12, 40])
+def test_fused_rmsnorm_prologue(lib, cuda, m):
+    """y = W . rmsnorm(x) with the norm folded into the GEMM (zl_w4a16_gemm_fused, ln_weight != NULL)."""
+    from zhilight_b200 import ops
+    k, n = 1024, 320
+    w, packed, _ = _setup(cuda, k, n, False, 12)
+    g = torch.Generator().manual_seed(6)
+    x = (torch.randn(m, k, generator=g) * 3.0).half()
+    lw = (1 + 0.1 * torch.randn(k, generator=g)).half()
+    y = ops.w4a16_gemm_fused(x.to(cuda), packed, n, k, ln_weight=lw.to(cuda), eps=1e-5).float().cpu().numpy()
+    xn = oops.rmsnorm(x.numpy(), lw.numpy(), 1e-5, 1.0, "f16")
+    ref = gptq.gemm_f32(xn, w)
+    assert rel_l2(y, ref) <= TOL
+    # and it matches the two-kernel path to the same tolerance
+    y2 = ops.w4a16_gemm(ops.rmsnorm(x.to(cuda), lw.to(cuda), 1e-5), packed, n, k).float().cpu().numpy()
+    assert rel_l2(y, y2) <= TOL
+
+
+def test_fused_rmsnorm_with_swiglu_and_many_tiles(lib, cuda):
+    """N large enough that persistent CTAs walk several super-tiles (grid = 2 per SM)."""
+    from zhilight_b200 import ops
+    k, f = 512, 5120                       # 2f/32 = 320 super-tiles > 296 CTAs
+    rm = ops.swiglu_row_map(f, cuda)
+    w, packed, _ = _setup(cuda, k, 2 * f, False, 13, rm)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(3, k, generator=g).half()
+    lw = (1 + 0.1 * torch.randn(k, generator=g)).half()
+    y = ops.w4a16_gemm_fused(x.to(cuda), packed, 2 * f, k, epilogue=ops.EPI_SWIGLU, ln_weight=lw.to(cuda),
+                             eps=1e-5).float().cpu().numpy()
+    xn = oops.rmsnorm(x.numpy(), lw.numpy(), 1e-5, 1.0, "f16")
+    full = gptq.gemm_f32(xn, w)
+    ref = oops.silu_mul(full[:, :f], full[:, f:], "f16")
+    assert rel_l2(y, ref) <= 2 * TOL
+
+
+@pytest.mark.parametrize("d,hq,hkv", [(128, 4, 2), (64, 4, 1)])
+def test_fused_qkv_rope_epilogue(lib, cuda, d, hq, hkv):
+    """qkv GEMM + split + RoPE + KV append in one kernel == GEMM, then rope_qk_cache, then copy_to_rag_buffer2."""
+    from zhilight_b200 import ops
+    k = 512
+    n = (hq + 2 * hkv) * d
+    rm = ops.qkv_rope_row_map(hq + 2 * hkv, d, cuda)
+    w, packed, _ = _setup(cuda, k, n, False, 14, rm)
+    w_plain, packed_plain, _ = _setup(cuda, k, n, False, 14)
+    g = torch.Generator().manual_seed(8)
+    t = 5
+    x = torch.randn(t, k, generator=g).half().to(cuda)
+    bias = torch.randn(n, generator=g).half().to(cuda)
+    pos = torch.tensor([0, 3, 7, 2, 9], dtype=torch.int32, device=cuda)
+    cos, sin = ops.rope_cos_sin(pos, d, 10000.0)
+    tb = torch.tensor([0, 1, 2, 1, 0], dtype=torch.int32, device=cuda)
+    pl = torch.tensor([0, 3, 7, 2, -1], dtype=torch.int32, device=cuda)
+    cap = 12
+    kb = [torch.zeros(cap, hkv, d, dtype=torch.float16, device=cuda) for _ in range(3)]
+    vb = [torch.zeros(cap, hkv, d, dtype=torch.float16, device=cuda) for _ in range(3)]
+    q = ops.w4a16_gemm_fused(x, packed, n, k, bias=ops.gather_rows_16(bias, rm), epilogue=ops.EPI_QKV_ROPE,
+                             rope=dict(cos=cos, sin=sin, token_batch=tb, placement=pl, k_bufs=kb, v_bufs=vb,
+                                       num_heads=hq, num_kv_heads=hkv, dim_head=d))
+    # unfused path on the same weights (natural row order)
+    qkv = ops.w4a16_gemm(x, packed_plain, n, k, bias=bias)
+    kb2 = [torch.zeros_like(b) for b in kb]
+    vb2 = [torch.zeros_like(b) for b in vb]
+    q2 = ops.qkv_rope_append(cos, sin, qkv, tb, pl, kb2, vb2, hq, hkv, d)
+    torch.testing.assert_close(q, q2, rtol=2 ** -9, atol=2e-3)
+    for a, b in zip(kb + vb, kb2 + vb2):
+        torch.testing.assert_close(a, b, rtol=2 ** -9, atol=2e-3)
+    assert kb[0][0].abs().sum() > 0 and vb[2][7].abs().sum() > 0

@@ -33,7 +33,22 @@ class LlamaConfig(ctypes.Structure):
         ("quant_type", ctypes.c_int), ("group_size", ctypes.c_int), ("sym", ctypes.c_int),
         ("dtype", ctypes.c_int), ("max_batch", ctypes.c_int), ("max_seq", ctypes.c_int),
         ("tp_rank", ctypes.c_int), ("tp_size", ctypes.c_int),
-        ("use_pdl", ctypes.c_int), ("use_graph", ctypes.c_int),
+        ("use_pdl", ctypes.c_int), ("use_graph", ctypes.c_int), ("fuse", ctypes.c_int),
+    ]
+
+
+class W4FusedArgs(ctypes.Structure):
+    """zl_w4_fused_args_t"""
+    _fields_ = [
+        ("x", ctypes.c_void_p), ("ldx", ctypes.c_int), ("packed", ctypes.c_void_p), ("bias", ctypes.c_void_p),
+        ("residual", ctypes.c_void_p), ("y", ctypes.c_void_p),
+        ("M", ctypes.c_int), ("N", ctypes.c_int), ("K", ctypes.c_int), ("group_size", ctypes.c_int),
+        ("epilogue", ctypes.c_int), ("pdl", ctypes.c_int),
+        ("ln_weight", ctypes.c_void_p), ("eps", ctypes.c_float),
+        ("cos", ctypes.c_void_p), ("sin", ctypes.c_void_p), ("q_out", ctypes.c_void_p),
+        ("token_batch", ctypes.c_void_p), ("placement", ctypes.c_void_p), ("k_addrs", ctypes.c_void_p),
+        ("v_addrs", ctypes.c_void_p),
+        ("num_heads", ctypes.c_int), ("num_kv_heads", ctypes.c_int), ("dim_head", ctypes.c_int),
     ]
 
 
@@ -66,6 +81,7 @@ def parse_header(path=HEADER):
     src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
     src = re.sub(r"//[^\n]*", " ", src)
     src = re.sub(r"typedef struct zl_llama_config \{.*?\} zl_llama_config_t;", " ", src, flags=re.S)
+    src = re.sub(r"typedef struct zl_w4_fused_args \{.*?\} zl_w4_fused_args_t;", " ", src, flags=re.S)
     protos = {}
     for m in re.finditer(r"([A-Za-z_][\w \*]*?)\b(zl_\w+)\s*\(([^;{}]*?)\)\s*;", src):
         ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()

@@ -238,7 +238,7 @@ static int attn_num_splits(int B, int len_q, int num_kv_heads, int m_query, int 
     const int base = B * len_q * num_kv_heads * hgroups;
     const int min_splits = cdiv(max_len_buf, kAttnMaxRange);
     const int want = cdiv(2 * 148, base);
-    const int max_useful = cdiv(max_len_buf, 128) > 0 ? cdiv(max_len_buf, 128) : 1;
+    const int max_useful = cdiv(max_len_buf, 256) > 0 ? cdiv(max_len_buf, 256) : 1;   // >= 256 keys per split
     int s = want < max_useful ? want : max_useful;
     if (s > kAttnMaxSplits) s = kAttnMaxSplits;
     if (s < min_splits) s = min_splits;

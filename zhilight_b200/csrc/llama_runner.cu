@@ -66,7 +66,8 @@ struct zl_llama {
     size_t attn_ws_bytes = 0;
     void* argmax_ws = nullptr;
     int32_t* h_stage = nullptr;   // pinned: tokens | pos | lens | next
-    std::map<int, cudaGraphExec_t> graphs;
+    std::map<long long, cudaGraphExec_t> graphs;   // key = B * 2^32 + attention length bucket
+    int cur_max_len = 0;                            // host-side upper bound of buf_lens (positions + 1)
     double weight_bytes = 0;
     int kernels_per_step = 0;
 };
@@ -174,7 +175,7 @@ int to_k_major(zl_llama* m, const std::string& prefix, int K, int N, uint32_t* q
 }
 
 int build_w4(zl_llama* m, const std::vector<std::string>& prefixes, const std::vector<int>& ns, int K, bool swiglu,
-             W4Lin* out) {
+             W4Lin* out, bool qkv_rope = false) {
     int N = 0;
     for (int n : ns) N += n;
     const int G = K / m->cfg.group_size;
@@ -196,6 +197,9 @@ int build_w4(zl_llama* m, const std::vector<std::string>& prefixes, const std::v
         RCHECK(dmalloc((void**)&row_map, (size_t)N * 4));
         k_swiglu_row_map<<<cdiv(N, 256), 256, 0, m->stream>>>(row_map, N / 2);
         ZL_CHECK_LAUNCH();
+    } else if (qkv_rope) {
+        RCHECK(dmalloc((void**)&row_map, (size_t)N * 4));
+        RCHECK(zl_qkv_rope_row_map(row_map, N / m->cfg.dim_head, m->cfg.dim_head, m->stream));
     }
     const size_t pbytes = zl_w4_packed_bytes(N, K, m->cfg.group_size);
     ZL_CHECK_SUPPORTED(pbytes > 0);
@@ -211,6 +215,14 @@ int build_w4(zl_llama* m, const std::vector<std::string>& prefixes, const std::v
                 ZL_CHECK_CUDA(cudaMemcpyAsync((char*)out->bias + (size_t)off * 2, b->ptr, (size_t)ns[i] * 2,
                                               cudaMemcpyDeviceToDevice, m->stream));
             off += ns[i];
+        }
+        if (row_map) {   // the fused epilogues index bias by packed row
+            void* pb = nullptr;
+            RCHECK(dmalloc(&pb, (size_t)N * 2));
+            RCHECK(zl_gather_rows_16(out->bias, row_map, pb, N, m->stream));
+            ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+            cudaFree(out->bias);
+            out->bias = pb;
         }
     }
     ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
@@ -296,7 +308,7 @@ int finalize_layer(zl_llama* m, int l) {
     const std::vector<std::string> gu = {p + "ff.w_in", p + "ff.w_gated"};
     const std::vector<int> gu_n = {m->ff, m->ff};
     if (c.quant_type == 5 || c.quant_type == 6) {
-        RCHECK(build_w4(m, qkv, qkv_n, D, false, &L.q_qkv));
+        RCHECK(build_w4(m, qkv, qkv_n, D, false, &L.q_qkv, c.fuse >= 2));
         RCHECK(build_w4(m, {p + "attn.attn_out"}, {D}, m->hq * d, false, &L.q_o));
         RCHECK(build_w4(m, gu, gu_n, D, true, &L.q_gu));
         RCHECK(build_w4(m, {p + "ff.w_out"}, {D}, m->ff, false, &L.q_down));
@@ -364,7 +376,42 @@ int alloc_runtime(zl_llama* m) {
 }
 
 // The decode-step kernel chain (captured into a graph by run_step).
-int enqueue_step(zl_llama* m, int B) {
+// cfg.fuse: 0 = one kernel per reference operator; 1 = RMSNorm folded into the following W4 GEMM;
+//           2 = additionally qkv split + RoPE + KV append folded into the qkv GEMM epilogue.
+int w4_gemm(zl_llama* m, const void* x, int ldx, const W4Lin& w, const void* residual, void* y, int B, int epi,
+            const void* ln_w, const Layer* rope_layer) {
+    const auto& c = m->cfg;
+    zl_w4_fused_args_t a = {};
+    a.x = x;
+    a.ldx = ldx;
+    a.packed = w.packed;
+    a.bias = w.bias;
+    a.residual = residual;
+    a.y = y;
+    a.M = B;
+    a.N = w.N;
+    a.K = w.K;
+    a.group_size = c.group_size;
+    a.epilogue = epi;
+    a.pdl = c.use_pdl;
+    a.ln_weight = ln_w;
+    a.eps = c.eps;
+    if (rope_layer) {
+        a.cos = m->cosb;
+        a.sin = m->sinb;
+        a.q_out = m->q;
+        a.token_batch = m->d_iota;
+        a.placement = m->d_pos;
+        a.k_addrs = rope_layer->k_addrs;
+        a.v_addrs = rope_layer->v_addrs;
+        a.num_heads = m->hq;
+        a.num_kv_heads = m->hkv;
+        a.dim_head = c.dim_head;
+    }
+    return zl_w4a16_gemm_fused(&a, m->stream);
+}
+
+int enqueue_step(zl_llama* m, int B, int len_bucket) {
     const auto& c = m->cfg;
     const int D = c.dim_model, d = c.dim_head, dt = c.dtype, pdl = c.use_pdl;
     cudaStream_t st = m->stream;
@@ -379,9 +426,19 @@ int enqueue_step(zl_llama* m, int B) {
     for (int l = 0; l < c.num_layers; ++l) {
         Layer& L = m->layers[l];
         if (w4) {
-            RCHECK(zl_rmsnorm(m->h, L.ln_attn, m->xn, B, D, c.eps, 1.f, dt, pdl, st));
-            RCHECK(zl_w4a16_gemm(m->xn, D, L.q_qkv.packed, L.q_qkv.bias, nullptr, m->qkv, B, L.q_qkv.N, D,
-                                 c.group_size, ZL_EPI_NONE, pdl, st));
+            const void* xin = m->xn;
+            const void* lnw = nullptr;
+            if (c.fuse >= 1) {
+                xin = m->h;
+                lnw = L.ln_attn;
+            } else {
+                RCHECK(zl_rmsnorm(m->h, L.ln_attn, m->xn, B, D, c.eps, 1.f, dt, pdl, st));
+            }
+            if (c.fuse >= 2) {
+                RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, nullptr, B, ZL_EPI_QKV_ROPE, lnw, &L));
+            } else {
+                RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, m->qkv, B, ZL_EPI_NONE, lnw, nullptr));
+            }
         } else {
             // residual of the previous layer's FFN is folded into this norm (block.cpp:139-141 + 131)
             RCHECK(zl_add_rmsnorm(m->h, l == 0 ? nullptr : m->pend, L.ln_attn, m->h, m->xn, B, D, c.eps, 1.f, 0, dt,
@@ -389,18 +446,23 @@ int enqueue_step(zl_llama* m, int B) {
             RCHECK(zl_dense_gemm_skinny(m->xn, D, L.d_qkv.w, L.d_qkv.bias, m->qkv, B, L.d_qkv.N, D, dt, dt, pdl,
                                         st));
         }
-        RCHECK(zl_qkv_rope_append(m->cosb, m->sinb, m->qkv, m->q, m->d_iota, m->d_pos, L.k_addrs, L.v_addrs, B,
-                                  m->hq, m->hkv, d, 1, 1, m->d_lens, dt, pdl, st));
-        RCHECK(zl_decode_attention(m->q, m->d_lens, L.k_addrs, L.v_addrs, nullptr, scale, c.max_seq, m->ao, B, 1,
+        if (!(w4 && c.fuse >= 2))
+            RCHECK(zl_qkv_rope_append(m->cosb, m->sinb, m->qkv, m->q, m->d_iota, m->d_pos, L.k_addrs, L.v_addrs, B,
+                                      m->hq, m->hkv, d, 1, 1, m->d_lens, dt, pdl, st));
+        RCHECK(zl_decode_attention(m->q, m->d_lens, L.k_addrs, L.v_addrs, nullptr, scale, len_bucket, m->ao, B, 1,
                                    m->hq, m->hkv, d, 1, m->attn_ws, m->attn_ws_bytes, dt, pdl, st));
         if (w4) {
-            RCHECK(zl_w4a16_gemm(m->ao, m->hq * d, L.q_o.packed, L.q_o.bias, m->h, m->h, B, D, m->hq * d,
-                                 c.group_size, ZL_EPI_RESIDUAL, pdl, st));
-            RCHECK(zl_rmsnorm(m->h, L.ln_ff, m->xn, B, D, c.eps, 1.f, dt, pdl, st));
-            RCHECK(zl_w4a16_gemm(m->xn, D, L.q_gu.packed, nullptr, nullptr, m->act, B, L.q_gu.N, D, c.group_size,
-                                 ZL_EPI_SWIGLU, pdl, st));
-            RCHECK(zl_w4a16_gemm(m->act, m->ff, L.q_down.packed, L.q_down.bias, m->h, m->h, B, D, m->ff,
-                                 c.group_size, ZL_EPI_RESIDUAL, pdl, st));
+            RCHECK(w4_gemm(m, m->ao, m->hq * d, L.q_o, m->h, m->h, B, ZL_EPI_RESIDUAL, nullptr, nullptr));
+            const void* xin = m->xn;
+            const void* lnw = nullptr;
+            if (c.fuse >= 1) {
+                xin = m->h;
+                lnw = L.ln_ff;
+            } else {
+                RCHECK(zl_rmsnorm(m->h, L.ln_ff, m->xn, B, D, c.eps, 1.f, dt, pdl, st));
+            }
+            RCHECK(w4_gemm(m, xin, D, L.q_gu, nullptr, m->act, B, ZL_EPI_SWIGLU, lnw, nullptr));
+            RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, m->h, m->h, B, ZL_EPI_RESIDUAL, nullptr, nullptr));
         } else {
             RCHECK(zl_dense_gemm_skinny(m->ao, m->hq * d, L.d_o.w, L.d_o.bias, m->pend, B, D, m->hq * d, dt, dt, pdl,
                                         st));
@@ -422,15 +484,22 @@ int enqueue_step(zl_llama* m, int B) {
     return ZL_OK;
 }
 
+// attention split counts are baked into the graph: one graph per (batch, length bucket)
+int len_bucket_of(const zl_llama* m, int max_len) {
+    int b = 256;
+    while (b < max_len) b <<= 1;
+    return b < m->cfg.max_seq ? b : (m->cfg.max_seq > 256 ? m->cfg.max_seq : 256);
+}
+
 int run_step(zl_llama* m, int B) {
-    if (!m->cfg.use_graph) return enqueue_step(m, B);
-    auto it = m->graphs.find(B);
+    const int bucket = len_bucket_of(m, m->cur_max_len);
+    if (!m->cfg.use_graph) return enqueue_step(m, B, bucket);
+    const long long key = ((long long)B << 32) | (unsigned)bucket;
+    auto it = m->graphs.find(key);
     if (it == m->graphs.end()) {
         cudaGraph_t graph = nullptr;
         ZL_CHECK_CUDA(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
-        const long long before = zl_launch_count(0);
-        int rc = enqueue_step(m, B);
-        const long long after = zl_launch_count(0);
+        int rc = enqueue_step(m, B, bucket);
         cudaError_t ce = cudaStreamEndCapture(m->stream, &graph);
         if (rc != ZL_OK) {
             if (graph) cudaGraphDestroy(graph);
@@ -442,10 +511,8 @@ int run_step(zl_llama* m, int B) {
         size_t n_nodes = 0;
         cudaGraphGetNodes(graph, nullptr, &n_nodes);
         m->kernels_per_step = (int)n_nodes;
-        (void)before;
-        (void)after;
         cudaGraphDestroy(graph);
-        it = m->graphs.emplace(B, exec).first;
+        it = m->graphs.emplace(key, exec).first;
     }
     ZL_CHECK_CUDA(cudaGraphLaunch(it->second, m->stream));
     return ZL_OK;
@@ -464,6 +531,8 @@ extern "C" int zl_llama_create(const zl_llama_config_t* cfg, zl_llama_t** out) {
     ZL_CHECK_SUPPORTED(cfg->tp_size >= 1 && cfg->tp_rank >= 0 && cfg->tp_rank < cfg->tp_size);
     ZL_CHECK_SUPPORTED(cfg->tp_size == 1);   // TP goes through zl_comm; not wired in the driver yet
     ZL_CHECK_SUPPORTED(cfg->quant_type == 0 || cfg->group_size == zl::kW4GroupK);
+    ZL_CHECK_ARG(cfg->fuse >= 0 && cfg->fuse <= 2);
+    ZL_CHECK_SUPPORTED(cfg->fuse < 2 || cfg->dim_head % 32 == 0);
     RCHECK(zl_prepare());
     zl_llama* m = new zl_llama();
     m->cfg = *cfg;
@@ -605,11 +674,14 @@ extern "C" int zl_llama_set_state(zl_llama_t* m, const int32_t* tokens_host, con
         zl_set_last_error(__FILE__, __LINE__, "model not finalized");
         return ZL_ERR_STATE;
     }
+    int mx = 0;
     for (int i = 0; i < B; ++i) {
         ZL_CHECK_ARG(positions_host[i] >= 0 && positions_host[i] < m->cfg.max_seq);
         m->h_stage[i] = tokens_host[i];
         m->h_stage[B + i] = positions_host[i];
+        if (positions_host[i] + 1 > mx) mx = positions_host[i] + 1;
     }
+    m->cur_max_len = mx;
     ZL_CHECK_CUDA(cudaMemcpyAsync(m->d_tokens, m->h_stage, B * 4, cudaMemcpyHostToDevice, m->stream));
     ZL_CHECK_CUDA(cudaMemcpyAsync(m->d_pos, m->h_stage + B, B * 4, cudaMemcpyHostToDevice, m->stream));
     return ZL_OK;
@@ -617,9 +689,14 @@ extern "C" int zl_llama_set_state(zl_llama_t* m, const int32_t* tokens_host, con
 
 extern "C" int zl_llama_step_device(zl_llama_t* m, int B) {
     ZL_CHECK_ARG(m && B > 0 && B <= m->cfg.max_batch);
+    if (m->cur_max_len >= m->cfg.max_seq) {
+        zl_set_last_error(__FILE__, __LINE__, "KV buffers full (max_seq reached)");
+        return ZL_ERR_STATE;
+    }
     RCHECK(run_step(m, B));
     k_advance<<<cdiv(B, 64), 64, 0, m->stream>>>(m->d_tokens, m->d_pos, m->d_next, B);
     ZL_CHECK_LAUNCH();
+    m->cur_max_len += 1;
     return ZL_OK;
 }
 

@@ -1,0 +1,34 @@
+// Kernel parameter block of the W4A16 GEMM variants (host + device).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace zl {
+
+struct W4Params {
+    const __half* x;
+    int ldx;
+    const uint8_t* packed;
+    const __half* bias;       // indexed by PACKED row
+    const __half* residual;
+    __half* y;
+    int mc, N, K, epi;
+    // fused RMSNorm prologue (ln_w == nullptr: off)
+    const __half* ln_w;
+    float eps;
+    // ZL_EPI_QKV_ROPE
+    const float* cos;
+    const float* sin;
+    __half* q_out;
+    const int32_t* token_batch;
+    const int32_t* placement;
+    __half* const* k_addrs;
+    __half* const* v_addrs;
+    int num_heads, num_kv_heads, dim_head;
+};
+
+cudaError_t launch_w4_v2(const W4Params& p, bool pdl, cudaStream_t stream);
+cudaError_t prepare_w4_v2();
+
+}  // namespace zl

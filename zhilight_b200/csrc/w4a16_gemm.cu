@@ -17,6 +17,9 @@
 //   * epilogue: cross-warp (split-k) reduction through shared memory, then bias / SwiGLU / residual.
 #include "common.cuh"
 #include "w4_layout.cuh"
+#include "w4_params.h"
+
+#include <cstdlib>
 
 namespace zl {
 
@@ -244,6 +247,96 @@ extern "C" int zl_prepare(void) {
     ZL_CHECK_CUDA(cudaFuncSetAttribute(k_w4a16_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kW4SmemBytes));
     ZL_CHECK_CUDA(cudaFuncSetAttribute(k_w4a16_mma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kW4SmemBytes));
     ZL_CHECK_CUDA(cudaFuncSetAttribute(k_w4a16_mma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kW4SmemBytes));
+    ZL_CHECK_CUDA(prepare_w4_v2());
+    return ZL_OK;
+}
+
+// ZL_W4_KERNEL=1 selects the first (non-persistent) variant for A/B measurements; default is v2.
+static int w4_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ZL_W4_KERNEL");
+        v = (e && e[0] == '1') ? 1 : 2;
+    }
+    return v;
+}
+
+namespace zl {
+__global__ void k_qkv_rope_row_map(int32_t* map, int n_rows, int d) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_rows) return;
+    const int tiles_per_head = d / 32;
+    const int st = p >> 5, head = st / tiles_per_head, jt = st % tiles_per_head;
+    const int r32 = p & 31, tt = r32 >> 4, r16 = r32 & 15;
+    const int c = jt * 16 + tt * 8 + (r16 & 7);
+    map[p] = head * d + c + ((r16 >= 8) ? d / 2 : 0);
+}
+__global__ void k_gather_16(const uint16_t* __restrict__ src, const int32_t* __restrict__ map, uint16_t* __restrict__ dst,
+                            int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[map[i]];
+}
+}  // namespace zl
+
+extern "C" int zl_qkv_rope_row_map(int32_t* row_map, int n_heads_total, int dim_head, zl_stream_t stream) {
+    ZL_CHECK_ARG(row_map && n_heads_total > 0 && dim_head > 0);
+    ZL_CHECK_SUPPORTED(dim_head % 32 == 0);
+    const int n = n_heads_total * dim_head;
+    k_qkv_rope_row_map<<<cdiv(n, 256), 256, 0, stream>>>(row_map, n, dim_head);
+    ZL_CHECK_LAUNCH();
+    return ZL_OK;
+}
+
+extern "C" int zl_gather_rows_16(const void* src, const int32_t* map, void* dst, int n, zl_stream_t stream) {
+    ZL_CHECK_ARG(src && map && dst && n > 0);
+    k_gather_16<<<cdiv(n, 256), 256, 0, stream>>>((const uint16_t*)src, map, (uint16_t*)dst, n);
+    ZL_CHECK_LAUNCH();
+    return ZL_OK;
+}
+
+extern "C" int zl_w4a16_gemm_fused(const zl_w4_fused_args_t* a, zl_stream_t stream) {
+    ZL_CHECK_ARG(a && a->x && a->packed && a->M > 0 && a->N > 0 && a->K > 0);
+    ZL_CHECK_SUPPORTED(a->group_size == kW4GroupK);
+    ZL_CHECK_SUPPORTED(a->N % 32 == 0 && a->K % kW4GroupK == 0);
+    ZL_CHECK_ARG(a->ldx >= a->K && a->ldx % 8 == 0);
+    ZL_CHECK_ARG((reinterpret_cast<uintptr_t>(a->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->packed) & 15) == 0);
+    ZL_CHECK_ARG(a->epilogue >= ZL_EPI_NONE && a->epilogue <= ZL_EPI_QKV_ROPE);
+    ZL_CHECK_ARG(a->epilogue != ZL_EPI_RESIDUAL || a->residual != nullptr);
+    ZL_CHECK_ARG(a->epilogue == ZL_EPI_QKV_ROPE || a->y != nullptr);
+    ZL_CHECK_ARG(a->ln_weight == nullptr || (reinterpret_cast<uintptr_t>(a->ln_weight) & 15) == 0);
+    if (a->epilogue == ZL_EPI_QKV_ROPE) {
+        ZL_CHECK_ARG(a->cos && a->sin && a->q_out && a->token_batch && a->placement && a->k_addrs && a->v_addrs);
+        ZL_CHECK_ARG(a->num_heads > 0 && a->num_kv_heads > 0 && a->dim_head > 0);
+        ZL_CHECK_SUPPORTED(a->dim_head % 32 == 0);
+        ZL_CHECK_ARG(a->N == (a->num_heads + 2 * a->num_kv_heads) * a->dim_head);
+    }
+    const int n_out = a->epilogue == ZL_EPI_SWIGLU ? a->N / 2 : a->N;
+    for (int m0 = 0; m0 < a->M; m0 += 32) {
+        W4Params p;
+        p.mc = (a->M - m0) < 32 ? (a->M - m0) : 32;
+        p.x = static_cast<const __half*>(a->x) + (size_t)m0 * a->ldx;
+        p.ldx = a->ldx;
+        p.packed = static_cast<const uint8_t*>(a->packed);
+        p.bias = static_cast<const __half*>(a->bias);
+        p.residual = a->residual ? static_cast<const __half*>(a->residual) + (size_t)m0 * a->N : nullptr;
+        p.y = a->y ? static_cast<__half*>(a->y) + (size_t)m0 * n_out : nullptr;
+        p.N = a->N;
+        p.K = a->K;
+        p.epi = a->epilogue;
+        p.ln_w = static_cast<const __half*>(a->ln_weight);
+        p.eps = a->eps;
+        p.cos = a->cos ? a->cos + (size_t)m0 * a->dim_head : nullptr;
+        p.sin = a->sin ? a->sin + (size_t)m0 * a->dim_head : nullptr;
+        p.q_out = a->q_out ? static_cast<__half*>(a->q_out) + (size_t)m0 * a->num_heads * a->dim_head : nullptr;
+        p.token_batch = a->token_batch ? a->token_batch + m0 : nullptr;
+        p.placement = a->placement ? a->placement + m0 : nullptr;
+        p.k_addrs = reinterpret_cast<__half* const*>(a->k_addrs);
+        p.v_addrs = reinterpret_cast<__half* const*>(a->v_addrs);
+        p.num_heads = a->num_heads;
+        p.num_kv_heads = a->num_kv_heads;
+        p.dim_head = a->dim_head;
+        ZL_CHECK_CUDA(launch_w4_v2(p, a->pdl != 0 && m0 == 0, stream));
+    }
     return ZL_OK;
 }
 
@@ -257,6 +350,12 @@ extern "C" int zl_w4a16_gemm(const void* x, int ldx, const void* packed, const v
     ZL_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(packed) & 15) == 0);
     ZL_CHECK_ARG(epilogue == ZL_EPI_NONE || epilogue == ZL_EPI_SWIGLU || epilogue == ZL_EPI_RESIDUAL);
     ZL_CHECK_ARG(epilogue != ZL_EPI_RESIDUAL || residual != nullptr);
+    if (w4_variant() == 2) {
+        zl_w4_fused_args_t a = {};
+        a.x = x; a.ldx = ldx; a.packed = packed; a.bias = bias; a.residual = residual; a.y = y;
+        a.M = M; a.N = N; a.K = K; a.group_size = group_size; a.epilogue = epilogue; a.pdl = pdl;
+        return zl_w4a16_gemm_fused(&a, stream);
+    }
     const int n_out = epilogue == ZL_EPI_SWIGLU ? N / 2 : N;
     const __half* xp = static_cast<const __half*>(x);
     const __half* rp = static_cast<const __half*>(residual);

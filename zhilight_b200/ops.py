@@ -10,7 +10,7 @@ import torch
 from . import _lib
 
 F16, BF16, F32 = 0, 1, 2
-EPI_NONE, EPI_SWIGLU, EPI_RESIDUAL = 0, 1, 2
+EPI_NONE, EPI_SWIGLU, EPI_RESIDUAL, EPI_QKV_ROPE = 0, 1, 2, 3
 
 
 def _dt(t):
@@ -144,6 +144,56 @@ def w4a16_gemm(x, packed, n, k, group_size=128, bias=None, residual=None, epilog
     _lib.call("zl_w4a16_gemm", _p(x), x.stride(0), _p(packed), _p(bias), _p(residual), _p(out), m, n, k, group_size,
               epilogue, int(pdl), _stream())
     return out
+
+
+def _dp(t):
+    return t.data_ptr() if t is not None else None
+
+
+def qkv_rope_row_map(n_heads_total, dim_head, device):
+    m = torch.empty(n_heads_total * dim_head, dtype=torch.int32, device=device)
+    _lib.call("zl_qkv_rope_row_map", _p(m), n_heads_total, dim_head, _stream())
+    return m
+
+
+def gather_rows_16(src, row_map):
+    dst = torch.empty(row_map.numel(), dtype=src.dtype, device=src.device)
+    _lib.call("zl_gather_rows_16", _p(src), _p(row_map), _p(dst), row_map.numel(), _stream())
+    return dst
+
+
+def w4a16_gemm_fused(x, packed, n, k, group_size=128, bias=None, residual=None, epilogue=EPI_NONE, pdl=False, out=None,
+                     ln_weight=None, eps=1e-5, rope=None):
+    """zl_w4a16_gemm_fused.  rope = dict(cos, sin, token_batch, placement, k_bufs, v_bufs, num_heads, num_kv_heads,
+    dim_head) for EPI_QKV_ROPE (returns q); bias must be in packed-row order."""
+    if x.dtype != torch.float16:
+        raise _lib.ZLError(-2, "A must be half")
+    m = x.shape[0]
+    a = _lib.W4FusedArgs()
+    a.x, a.ldx, a.packed, a.bias, a.residual = x.data_ptr(), x.stride(0), packed.data_ptr(), _dp(bias), _dp(residual)
+    a.M, a.N, a.K, a.group_size, a.epilogue, a.pdl = m, n, k, group_size, epilogue, int(pdl)
+    a.ln_weight, a.eps = _dp(ln_weight), eps
+    keep = []
+    if epilogue == EPI_QKV_ROPE:
+        r = rope
+        q = torch.empty((m, r["num_heads"] * r["dim_head"]), dtype=torch.float16, device=x.device)
+        ka, va = _ptr_table(r["k_bufs"], x.device), _ptr_table(r["v_bufs"], x.device)
+        keep += [ka, va]
+        a.cos, a.sin, a.q_out = r["cos"].data_ptr(), r["sin"].data_ptr(), q.data_ptr()
+        a.token_batch, a.placement = r["token_batch"].data_ptr(), r["placement"].data_ptr()
+        a.k_addrs, a.v_addrs = ka.data_ptr(), va.data_ptr()
+        a.num_heads, a.num_kv_heads, a.dim_head = r["num_heads"], r["num_kv_heads"], r["dim_head"]
+        ret = q
+    else:
+        n_out = n // 2 if epilogue == EPI_SWIGLU else n
+        if out is None:
+            out = torch.empty((m, n_out), dtype=torch.float16, device=x.device)
+        a.y = out.data_ptr()
+        ret = out
+    _lib.call("zl_w4a16_gemm_fused", ctypes.byref(a), _stream())
+    if keep:
+        torch.cuda.current_stream().synchronize()
+    return ret
 
 
 def dense_gemm_skinny(x, w, bias=None, out_dtype=None, pdl=False):
