@@ -27,7 +27,7 @@ def to_bf16_bits(x):
 
 
 class OracleLlama:
-    def __init__(self, cfg, state_dict, quant_type=0, group_size=128, sym=False, dtype="f16"):
+    def __init__(self, cfg, state_dict, quant_type=0, group_size=128, sym=False, dtype="f16", fuse_norm=False):
         """cfg: dict with num_layers, dim_model, num_heads, num_kv_heads, dim_head, dim_ff, vocab_size, eps,
         rope_theta, rope_llama3.  state_dict: HF/ZhiLight-named numpy tensors."""
         self.c = dict(cfg)
@@ -36,6 +36,9 @@ class OracleLlama:
         self.quant_type = quant_type
         self.group_size = group_size
         self.sym = sym
+        # fuse_norm=True restates OUR fused kernel's rounding points (x*w_ln rounded to T feeds the GEMM, the
+        # fp32 accumulator is scaled by rsqrt(mean(x^2)+eps)); False is the reference's operator order.
+        self.fuse_norm = fuse_norm and quant_type in (5, 6)
         self.w = {}
         self.kv = {}          # task -> list over layers of (k (cap,Hkv,d), v)
 
@@ -64,6 +67,24 @@ class OracleLlama:
             y = y + _f32(b, self.dtype)[None, :]
         return ops._t(y, self.dtype)
 
+    def _norm_linears(self, h, ln_w, prefixes):
+        """[T(W_i . rmsnorm(h))] for several Linears sharing one RMSNorm'd input."""
+        c, T = self.c, self.dtype
+        if not self.fuse_norm:
+            xn = ops.rmsnorm(h, ln_w, c["eps"], 1.0, T)
+            return [self._linear(xn, p) for p in prefixes]
+        h = np.asarray(h, F32)
+        xw = ops._t(h * np.asarray(ln_w, F32), T)
+        rstd = F32(1.0) / np.sqrt((h * h).sum(-1, keepdims=True, dtype=F32) / F32(h.shape[-1]) + F32(c["eps"]))
+        outs = []
+        for p in prefixes:
+            y = (xw @ self._weight(p).T) * rstd
+            b = self.sd.get(p + ".bias")
+            if b is not None:
+                y = y + _f32(b, T)[None, :]
+            outs.append(ops._t(y, T))
+        return outs
+
     def decode(self, tokens, positions, tasks=None):
         """One step for B tasks; returns logits (B, V) fp32.  Task b appends its K/V at positions[b]."""
         c, T = self.c, self.dtype
@@ -76,10 +97,8 @@ class OracleLlama:
         scale = F32(1.0 / np.sqrt(d))
         for l in range(c["num_layers"]):
             p = "layers.%d." % l
-            xn = ops.rmsnorm(h, _f32(self.sd[p + "ln_attn.weight"], T), c["eps"], 1.0, T)
-            q = self._linear(xn, p + "attn.project_q")
-            k = self._linear(xn, p + "attn.project_k")
-            v = self._linear(xn, p + "attn.project_v")
+            q, k, v = self._norm_linears(h, _f32(self.sd[p + "ln_attn.weight"], T),
+                                         [p + "attn.project_q", p + "attn.project_k", p + "attn.project_v"])
             qkv = np.concatenate([q, k, v], axis=1)
             q, k, v = ops.split_qkv_rope(qkv, cos, sin, hq, hkv, d, True, T)
             ao = np.zeros((b, hq * d), F32)
@@ -101,9 +120,7 @@ class OracleLlama:
                 ao[i] = o.reshape(-1)
             o = self._linear(ao, p + "attn.attn_out")
             h = ops.residual_add(h, o, T)
-            xn = ops.rmsnorm(h, _f32(self.sd[p + "ln_ff.weight"], T), c["eps"], 1.0, T)
-            g = self._linear(xn, p + "ff.w_in")
-            u = self._linear(xn, p + "ff.w_gated")
+            g, u = self._norm_linears(h, _f32(self.sd[p + "ln_ff.weight"], T), [p + "ff.w_in", p + "ff.w_gated"])
             act = ops.silu_mul(g, u, T)
             dn = self._linear(act, p + "ff.w_out")
             h = ops.residual_add(h, dn, T)

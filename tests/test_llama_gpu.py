@@ -21,7 +21,7 @@ def _run(cfg, quant, dtype, sym=False, use_pdl=True, use_graph=True, steps=6, ti
     dec = LlamaDecoder(quant_type=quant, group_size=128, sym=sym, dtype=dtype, max_batch=3, max_seq=64,
                        use_pdl=use_pdl, use_graph=use_graph, fuse=fuse, **cfg)
     dec.load_state_dict(sd)
-    orc = omodel.OracleLlama(cfg, sd, quant, 128, sym, dtype)
+    orc = omodel.OracleLlama(cfg, sd, quant, 128, sym, dtype, fuse_norm=fuse >= 1)
     rng = np.random.default_rng(seed)
     # three tasks at different positions (ragged batch, like the dynamic batcher produces)
     pos = np.array([0, 0, 0], dtype=np.int32)
@@ -106,7 +106,7 @@ def test_long_context_crosses_attention_buckets(lib, cuda):
     sd = omodel.make_state_dict(TINY, 5, 128, False, seed=5)
     dec = LlamaDecoder(quant_type=5, max_batch=1, max_seq=600, **TINY)
     dec.load_state_dict(sd)
-    orc = omodel.OracleLlama(TINY, sd, 5, 128, False, "f16")
+    orc = omodel.OracleLlama(TINY, sd, 5, 128, False, "f16", fuse_norm=True)
     rng = np.random.default_rng(0)
     toks = rng.integers(0, TINY["vocab_size"], size=300).astype(np.int32)
     for p in range(300):

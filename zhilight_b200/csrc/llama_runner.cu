@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "w4_layout.cuh"
 
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -411,8 +412,20 @@ int w4_gemm(zl_llama* m, const void* x, int ldx, const W4Lin& w, const void* res
     return zl_w4a16_gemm_fused(&a, m->stream);
 }
 
+// ZL_DEBUG_SKIP (bit mask, timing experiments only -- results are wrong when set):
+// 1 attention, 2 qkv GEMM, 4 o GEMM, 8 gate/up GEMM, 16 down GEMM, 32 lm_head, 64 rope/append kernel
+static int debug_skip() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ZL_DEBUG_SKIP");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
 int enqueue_step(zl_llama* m, int B, int len_bucket) {
     const auto& c = m->cfg;
+    const int skip = debug_skip();
     const int D = c.dim_model, d = c.dim_head, dt = c.dtype, pdl = c.use_pdl;
     cudaStream_t st = m->stream;
     const bool w4 = c.quant_type == 5 || c.quant_type == 6;
@@ -434,7 +447,8 @@ int enqueue_step(zl_llama* m, int B, int len_bucket) {
             } else {
                 RCHECK(zl_rmsnorm(m->h, L.ln_attn, m->xn, B, D, c.eps, 1.f, dt, pdl, st));
             }
-            if (c.fuse >= 2) {
+            if (skip & 2) {
+            } else if (c.fuse >= 2) {
                 RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, nullptr, B, ZL_EPI_QKV_ROPE, lnw, &L));
             } else {
                 RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, m->qkv, B, ZL_EPI_NONE, lnw, nullptr));
@@ -446,13 +460,15 @@ int enqueue_step(zl_llama* m, int B, int len_bucket) {
             RCHECK(zl_dense_gemm_skinny(m->xn, D, L.d_qkv.w, L.d_qkv.bias, m->qkv, B, L.d_qkv.N, D, dt, dt, pdl,
                                         st));
         }
-        if (!(w4 && c.fuse >= 2))
+        if (!(w4 && c.fuse >= 2) && !(skip & 64))
             RCHECK(zl_qkv_rope_append(m->cosb, m->sinb, m->qkv, m->q, m->d_iota, m->d_pos, L.k_addrs, L.v_addrs, B,
                                       m->hq, m->hkv, d, 1, 1, m->d_lens, dt, pdl, st));
-        RCHECK(zl_decode_attention(m->q, m->d_lens, L.k_addrs, L.v_addrs, nullptr, scale, len_bucket, m->ao, B, 1,
-                                   m->hq, m->hkv, d, 1, m->attn_ws, m->attn_ws_bytes, dt, pdl, st));
+        if (!(skip & 1))
+            RCHECK(zl_decode_attention(m->q, m->d_lens, L.k_addrs, L.v_addrs, nullptr, scale, len_bucket, m->ao, B, 1,
+                                       m->hq, m->hkv, d, 1, m->attn_ws, m->attn_ws_bytes, dt, pdl, st));
         if (w4) {
-            RCHECK(w4_gemm(m, m->ao, m->hq * d, L.q_o, m->h, m->h, B, ZL_EPI_RESIDUAL, nullptr, nullptr));
+            if (!(skip & 4))
+                RCHECK(w4_gemm(m, m->ao, m->hq * d, L.q_o, m->h, m->h, B, ZL_EPI_RESIDUAL, nullptr, nullptr));
             const void* xin = m->xn;
             const void* lnw = nullptr;
             if (c.fuse >= 1) {
@@ -461,8 +477,9 @@ int enqueue_step(zl_llama* m, int B, int len_bucket) {
             } else {
                 RCHECK(zl_rmsnorm(m->h, L.ln_ff, m->xn, B, D, c.eps, 1.f, dt, pdl, st));
             }
-            RCHECK(w4_gemm(m, xin, D, L.q_gu, nullptr, m->act, B, ZL_EPI_SWIGLU, lnw, nullptr));
-            RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, m->h, m->h, B, ZL_EPI_RESIDUAL, nullptr, nullptr));
+            if (!(skip & 8)) RCHECK(w4_gemm(m, xin, D, L.q_gu, nullptr, m->act, B, ZL_EPI_SWIGLU, lnw, nullptr));
+            if (!(skip & 16))
+                RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, m->h, m->h, B, ZL_EPI_RESIDUAL, nullptr, nullptr));
         } else {
             RCHECK(zl_dense_gemm_skinny(m->ao, m->hq * d, L.d_o.w, L.d_o.bias, m->pend, B, D, m->hq * d, dt, dt, pdl,
                                         st));
@@ -479,7 +496,8 @@ int enqueue_step(zl_llama* m, int B, int len_bucket) {
     } else {
         RCHECK(zl_add_rmsnorm(m->h, m->pend, m->ln_f, m->h, m->xn, B, D, c.eps, 1.f, 0, dt, pdl, st));
     }
-    RCHECK(zl_dense_gemm_skinny(m->xn, D, m->lm_head, nullptr, m->logits, B, c.vocab_size, D, dt, ZL_F32, pdl, st));
+    if (!(skip & 32))
+        RCHECK(zl_dense_gemm_skinny(m->xn, D, m->lm_head, nullptr, m->logits, B, c.vocab_size, D, dt, ZL_F32, pdl, st));
     RCHECK(zl_argmax(m->logits, m->d_next, B, c.vocab_size, m->argmax_ws, zl_argmax_workspace_bytes(B), pdl, st));
     return ZL_OK;
 }

@@ -295,6 +295,12 @@ extern "C" int zl_gather_rows_16(const void* src, const int32_t* map, void* dst,
 }
 
 extern "C" int zl_w4a16_gemm_fused(const zl_w4_fused_args_t* a, zl_stream_t stream) {
+    static bool prepared = false;
+    if (!prepared) {
+        int rc = zl_prepare();
+        if (rc != ZL_OK) return rc;
+        prepared = true;
+    }
     ZL_CHECK_ARG(a && a->x && a->packed && a->M > 0 && a->N > 0 && a->K > 0);
     ZL_CHECK_SUPPORTED(a->group_size == kW4GroupK);
     ZL_CHECK_SUPPORTED(a->N % 32 == 0 && a->K % kW4GroupK == 0);

@@ -18,20 +18,28 @@
 
 namespace zl {
 
-constexpr int kV2Warps = 8;
-constexpr int kV2Stages = 4;
-constexpr int kV2RingBytes = kV2Warps * kV2Stages * kW4BlockBytes;
-
-template <int NT>
+// Two shapes of CTA (picked per GEMM by the number of 32-row super-tiles):
+//   wide  : 8 warps, 5-stage rings, 2 CTAs/SM, persistent over tiles        (N/32 > #SMs: qkv, gate/up)
+//   tall  : 16 warps, 4-stage rings, 1 CTA/SM, k split 16 ways              (N/32 <= #SMs: o_proj, down)
+// Either way ~140-170 KB of weights are in flight per SM, which is what it takes to cover the ~2 us loaded
+// HBM latency at 6.5 TB/s (Little's law: 13 MB chip-wide).
+template <int NT, int WARPS, int STAGES>
 struct V2Smem {
-    static constexpr int kRedBufs = NT == 1 ? 2 : 1;
-    static constexpr int kRedFloats = kV2Warps * NT * 8 * 32;
-    static constexpr int kBarOff = kV2RingBytes;
-    static constexpr int kRedOff = kBarOff + kV2Warps * kV2Stages * 8;
-    static constexpr int kSsOff = kRedOff + kRedBufs * kRedFloats * 4;          // [8 warps][NT*8] sum of squares
-    static constexpr int kRstdOff = kSsOff + kV2Warps * NT * 8 * 4;             // [NT*8]
-    static constexpr int kBytes = kRstdOff + NT * 8 * 4;
+    static constexpr int kRingBytes = WARPS * STAGES * kW4BlockBytes;
+    static constexpr int kRedBufs = (NT == 1 && WARPS == 8) ? 2 : 1;
+    static constexpr int kRedFloats = WARPS * NT * 8 * 32;
+    static constexpr int kBarOff = kRingBytes;
+    static constexpr int kRedOff = kBarOff + WARPS * STAGES * 8;
+    static constexpr int kSsOff = kRedOff + kRedBufs * kRedFloats * 4;          // [warps][NT*8] sum of squares
+    static constexpr int kRstdOff = kSsOff + WARPS * NT * 8 * 4;                // [NT*8]
+    static constexpr int kXOff = (kRstdOff + NT * 8 * 4 + 127) & ~127;          // optional x cache [mc][K + 32] halves
+    static constexpr int kBytes = kXOff;
 };
+// (dynamic smem budgets)
+// largest dynamic smem that still lets two CTAs share an SM (227 KB usable, 1 KB reserved per CTA) / one CTA
+constexpr int kV2TwoCtaBudget = 115000;
+constexpr int kV2OneCtaBudget = 231000;
+__host__ __device__ inline int x_row_bytes(int K) { return K * 2 + 64; }   // +64 B: conflict-free LDS.128 across tokens
 
 template <int NT, bool NORM>
 __device__ __forceinline__ void load_bfrag_v2(uint4 (&b)[NT][4], const W4Params& p, int kbase, int g, int t,
@@ -70,9 +78,11 @@ __device__ __forceinline__ void load_bfrag_v2(uint4 (&b)[NT][4], const W4Params&
     }
 }
 
-template <int NT, bool NORM>
-__global__ void __launch_bounds__(kV2Warps * 32, (NT <= 2 ? 2 : 1)) k_w4a16_v2(const W4Params p) {
-    using S = V2Smem<NT>;
+template <int NT, bool NORM, bool XC, int WARPS, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32, ((NT <= 2 && WARPS == 8) ? 2 : 1)) k_w4a16_v2(const W4Params p) {
+    using S = V2Smem<NT, WARPS, STAGES>;
+    constexpr int kV2Warps = WARPS;
+    constexpr int kV2Stages = STAGES;
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -112,6 +122,46 @@ __global__ void __launch_bounds__(kV2Warps * 32, (NT <= 2 ? 2 : 1)) k_w4a16_v2(c
     __syncwarp();
     pdl_wait();   // weights above are constants; x / residual / KV below come from predecessor kernels
 
+    // ---- optional: stage x (times the RMSNorm weight) in shared memory once per CTA ----
+    uint8_t* xs = smem + S::kXOff;
+    const int xrow = x_row_bytes(p.K);
+    if (XC) {
+        const int chunks = p.K / 8;   // 16-byte chunks per token row
+        for (int tok = 0; tok < p.mc; ++tok) {
+            float sq = 0.f;
+            for (int ch = threadIdx.x; ch < chunks; ch += blockDim.x) {
+                uint4 v = ld_cg_u4(p.x + (size_t)tok * p.ldx + ch * 8);
+                if (NORM) {
+                    const uint4 wv = *reinterpret_cast<const uint4*>(p.ln_w + ch * 8);
+                    __half2* hv = reinterpret_cast<__half2*>(&v);
+                    const __half2* hw = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = __half22float2(hv[e]);
+                        sq = fmaf(f.x, f.x, sq);
+                        sq = fmaf(f.y, f.y, sq);
+                        hv[e] = __hmul2(hv[e], hw[e]);
+                    }
+                }
+                *reinterpret_cast<uint4*>(xs + (size_t)tok * xrow + ch * 16) = v;
+            }
+            if (NORM) {
+                sq = warp_sum(sq);
+                if (lane == 0) s_ss[warp * (NT * 8) + tok] = sq;
+            }
+        }
+        __syncthreads();
+        if (NORM) {
+            if (threadIdx.x < p.mc) {
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < kV2Warps; ++w) v += s_ss[w * (NT * 8) + threadIdx.x];
+                s_rstd[threadIdx.x] = rsqrtf(v / (float)p.K + p.eps);
+            }
+            __syncthreads();
+        }
+    }
+
     const __half2 one16 = __half2half2(__ushort_as_half((unsigned short)0x2c00));   // 1/16
     const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
     float ss[NT];
@@ -134,11 +184,25 @@ __global__ void __launch_bounds__(kV2Warps * 32, (NT <= 2 ? 2 : 1)) k_w4a16_v2(c
             const int s = it % kV2Stages;
             const uint32_t parity = (uint32_t)(it / kV2Stages) & 1u;
             uint4 bcur[NT][4];
-            // sum(x^2) only needs one pass over K: take it from the first tile
-            if (NORM && ti == 0)
+            if (XC) {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const int tok = nt * 8 + g;
+                    if (tok < p.mc) {
+                        const uint8_t* src = xs + (size_t)tok * xrow + ((g_begin + i) * kW4GroupK + t * 8) * 2;
+#pragma unroll
+                        for (int ii = 0; ii < 4; ++ii) bcur[nt][ii] = *reinterpret_cast<const uint4*>(src + ii * 64);
+                    } else {
+#pragma unroll
+                        for (int ii = 0; ii < 4; ++ii) bcur[nt][ii] = make_uint4(0, 0, 0, 0);
+                    }
+                }
+            } else if (NORM && ti == 0) {
+                // sum(x^2) only needs one pass over K: take it from the first tile
                 load_bfrag_v2<NT, NORM>(bcur, p, (g_begin + i) * kW4GroupK, g, t, ss);
-            else
+            } else {
                 load_bfrag_v2<NT, NORM>(bcur, p, (g_begin + i) * kW4GroupK, g, t, ss_dummy);
+            }
 
             mbar_wait(&bars[s], parity);
             const uint8_t* blk = ring + s * kW4BlockBytes;
@@ -212,7 +276,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, (NT <= 2 ? 2 : 1)) k_w4a16_v2(c
                 myred[tok * 32 + row + 8] = acc[tt][nt][2];
                 myred[(tok + 1) * 32 + row + 8] = acc[tt][nt][3];
             }
-        if (NORM && ti == 0) {
+        if (NORM && !XC && ti == 0) {
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
                 float v = ss[nt];
@@ -222,7 +286,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, (NT <= 2 ? 2 : 1)) k_w4a16_v2(c
             }
         }
         __syncthreads();
-        if (NORM && ti == 0) {
+        if (NORM && !XC && ti == 0) {
             if (threadIdx.x < NT * 8) {
                 float v = 0.f;
 #pragma unroll
@@ -323,15 +387,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, (NT <= 2 ? 2 : 1)) k_w4a16_v2(c
     }
 }
 
-template <int NT, bool NORM>
-static cudaError_t launch_v2_t(const W4Params& p, bool pdl, cudaStream_t stream) {
-    using S = V2Smem<NT>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_w4a16_v2<NT, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+static int v2_num_sms() {
     static int n_sm = 0;
     if (n_sm == 0) {
         int dev = 0;
@@ -339,25 +395,54 @@ static cudaError_t launch_v2_t(const W4Params& p, bool pdl, cudaStream_t stream)
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         if (n_sm <= 0) n_sm = 148;
     }
+    return n_sm;
+}
+
+template <int NT, bool NORM, bool XC, int WARPS, int STAGES>
+static cudaError_t launch_v2_t(const W4Params& p, bool pdl, cudaStream_t stream) {
+    using S = V2Smem<NT, WARPS, STAGES>;
+    const int smem = S::kBytes + (XC ? p.mc * x_row_bytes(p.K) : 0);
     const int tiles = p.N / 32;
-    const int max_ctas = n_sm * 2;
+    const int max_ctas = v2_num_sms() * (WARPS == 8 ? 2 : 1);
     const int grid = tiles < max_ctas ? tiles : max_ctas;
-    return launch(k_w4a16_v2<NT, NORM>, dim3(grid), dim3(kV2Warps * 32), (size_t)S::kBytes, stream, pdl, p);
+    return launch(k_w4a16_v2<NT, NORM, XC, WARPS, STAGES>, dim3(grid), dim3(WARPS * 32), (size_t)smem, stream, pdl, p);
+}
+
+template <int NT, int WARPS, int STAGES>
+static cudaError_t launch_v2_shape(const W4Params& p, bool pdl, cudaStream_t stream) {
+    const bool norm = p.ln_w != nullptr;
+    // stage x in shared memory when the CTA budget allows (always true for M = 1 at the Llama shapes)
+    const int budget = WARPS == 8 ? kV2TwoCtaBudget : kV2OneCtaBudget;
+    const bool xc = V2Smem<NT, WARPS, STAGES>::kBytes + p.mc * x_row_bytes(p.K) <= budget;
+    if (xc)
+        return norm ? launch_v2_t<NT, true, true, WARPS, STAGES>(p, pdl, stream)
+                    : launch_v2_t<NT, false, true, WARPS, STAGES>(p, pdl, stream);
+    return norm ? launch_v2_t<NT, true, false, WARPS, STAGES>(p, pdl, stream)
+                : launch_v2_t<NT, false, false, WARPS, STAGES>(p, pdl, stream);
+}
+
+template <int NT>
+static cudaError_t launch_v2_nt(const W4Params& p, bool pdl, cudaStream_t stream) {
+    const bool tall = NT <= 2 && p.N / 32 <= v2_num_sms() && p.K / kW4GroupK >= 32;
+    if (tall) return launch_v2_shape<(NT <= 2 ? NT : 1), 16, 4>(p, pdl, stream);
+    return launch_v2_shape<NT, 8, (NT == 1 ? 5 : 4)>(p, pdl, stream);
 }
 
 cudaError_t launch_w4_v2(const W4Params& p, bool pdl, cudaStream_t stream) {
-    const bool norm = p.ln_w != nullptr;
-    if (p.mc <= 8) return norm ? launch_v2_t<1, true>(p, pdl, stream) : launch_v2_t<1, false>(p, pdl, stream);
-    if (p.mc <= 16) return norm ? launch_v2_t<2, true>(p, pdl, stream) : launch_v2_t<2, false>(p, pdl, stream);
-    return norm ? launch_v2_t<4, true>(p, pdl, stream) : launch_v2_t<4, false>(p, pdl, stream);
+    if (p.mc <= 8) return launch_v2_nt<1>(p, pdl, stream);
+    if (p.mc <= 16) return launch_v2_nt<2>(p, pdl, stream);
+    return launch_v2_nt<4>(p, pdl, stream);
 }
 
 cudaError_t prepare_w4_v2() {
     cudaError_t e;
-#define ZL_SET(NT, NORM)                                                                                         \
-    e = cudaFuncSetAttribute(k_w4a16_v2<NT, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, V2Smem<NT>::kBytes); \
+#define ZL_SET(NT, NORM, XC, W, ST)                                                                                \
+    e = cudaFuncSetAttribute(k_w4a16_v2<NT, NORM, XC, W, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                             XC ? (W == 8 ? kV2TwoCtaBudget : kV2OneCtaBudget) : V2Smem<NT, W, ST>::kBytes);        \
     if (e != cudaSuccess) return e;
-    ZL_SET(1, false) ZL_SET(1, true) ZL_SET(2, false) ZL_SET(2, true) ZL_SET(4, false) ZL_SET(4, true)
+#define ZL_SET4(NT, W, ST) ZL_SET(NT, false, false, W, ST) ZL_SET(NT, true, false, W, ST) ZL_SET(NT, false, true, W, ST) ZL_SET(NT, true, true, W, ST)
+    ZL_SET4(1, 8, 5) ZL_SET4(2, 8, 4) ZL_SET4(4, 8, 4) ZL_SET4(1, 16, 4) ZL_SET4(2, 16, 4)
+#undef ZL_SET4
 #undef ZL_SET
     return cudaSuccess;
 }
