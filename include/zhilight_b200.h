@@ -88,6 +88,13 @@ size_t zl_w4_packed_bytes(int N, int K, int group_size);
 int zl_w4_pack(const uint32_t* qweight_km, const uint8_t* qzeros_km, const void* scales_km,
                const int32_t* row_map, void* packed, int N, int K, int group_size, int sym,
                zl_stream_t stream);
+/* variant 0: ZLW4 (fp16 HMMA kernels); variant 1: ZLW4I (exact-integer IMMA kernel, zl_w4a16_gemm_fused with
+ * args.variant = 1).  zl_w4_pack == variant 0. */
+int zl_w4_pack_v(const uint32_t* qweight_km, const uint8_t* qzeros_km, const void* scales_km,
+                 const int32_t* row_map, void* packed, int N, int K, int group_size, int sym, int variant,
+                 zl_stream_t stream);
+int zl_w4_unpack_v(const void* packed, uint32_t* qweight_km, uint8_t* qzeros_km, void* scales_km, int N, int K,
+                   int group_size, int variant, zl_stream_t stream);
 /* inverse (tests): recover k-major nibbles/zeros/scales from the packed form. */
 int zl_w4_unpack(const void* packed, uint32_t* qweight_km, uint8_t* qzeros_km, void* scales_km, int N, int K,
                  int group_size, zl_stream_t stream);
@@ -114,8 +121,11 @@ typedef struct zl_w4_fused_args {
     const float* cos; const float* sin; void* q_out;
     const int32_t* token_batch; const int32_t* placement; void* const* k_addrs; void* const* v_addrs;
     int num_heads, num_kv_heads, dim_head;
+    int variant; /* layout of `packed`: 0 ZLW4, 1 ZLW4I (integer kernel; needs the staged activations to fit smem) */
 } zl_w4_fused_args_t;
 int zl_w4a16_gemm_fused(const zl_w4_fused_args_t* args, zl_stream_t stream);
+/* 1 if the exact-integer kernel (variant 1) can run this shape: its staged activations must fit shared memory. */
+int zl_w4_int_kernel_fits(int M, int N, int K);
 /* row_map (n_heads_total*dim_head) for zl_w4_pack so that RoPE partners (c, c+d/2) share an MMA tile. */
 int zl_qkv_rope_row_map(int32_t* row_map, int n_heads_total, int dim_head, zl_stream_t stream);
 /* dst[i] = src[map[i]] for 16-bit elements (bias permutation to packed-row order). */

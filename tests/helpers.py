@@ -65,3 +65,32 @@ def to_bf16_bits(x):
 
 def from_bf16_bits(b):
     return (np.asarray(b, dtype=np.uint16).astype(np.uint32) << 16).view(np.float32)
+
+
+def w4i_pack_numpy(qw_km, qz_km, sc_km, sym=False, row_map=None):
+    """numpy restatement of the ZLW4I (integer-kernel) nibble order; meta identical to ZLW4."""
+    base = w4_pack_numpy(qw_km, qz_km, sc_km, sym, row_map).reshape(-1, BLK).copy()
+    q = gptq.unpack_k_major(qw_km)
+    if row_map is not None:
+        q = q[row_map]
+    n, k = q.shape
+    g = k // 128
+    qr = q.reshape(n // 32, 32, g, 128)
+    words = np.zeros((n // 32, g, 512), dtype=np.uint32)
+    for tt in range(2):
+        for hh in range(2):
+            for lane in range(32):
+                gg, t = lane >> 2, lane & 3
+                for jj in range(4):
+                    wi = hh * 4 + jj
+                    j, p = wi >> 1, wi & 1
+                    idx = ((tt * 2 + hh) * 32 + lane) * 4 + jj
+                    w = np.zeros((n // 32, g), dtype=np.uint32)
+                    for slot in range(8):
+                        row = tt * 16 + gg + (8 if slot & 1 else 0)
+                        kk = t * 32 + j * 8 + p * 4 + (slot >> 1)
+                        w |= qr[:, row, :, kk].astype(np.uint32) << np.uint32(4 * slot)
+                    words[:, :, idx] = w
+    base = base.reshape(n // 32, g, BLK)
+    base[:, :, :2048] = words.view(np.uint8).reshape(n // 32, g, 2048)
+    return base.reshape(-1)

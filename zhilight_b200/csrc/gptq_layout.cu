@@ -145,7 +145,7 @@ __global__ void k_dequant_k_major(const uint32_t* __restrict__ qw, const uint8_t
 // ---- ZLW4 packer: one thread per packed weight word; a few threads per block also write the meta ----
 __global__ void k_w4_pack(const uint32_t* __restrict__ qw, const uint8_t* __restrict__ qz,
                           const __half* __restrict__ sc, const int32_t* __restrict__ row_map,
-                          uint8_t* __restrict__ packed, int N, int K, int sym) {
+                          uint8_t* __restrict__ packed, int N, int K, int sym, int variant) {
     const int G = K / kW4GroupK;
     const int K8 = K / 8;
     const int st = blockIdx.x;       // super tile (32 rows)
@@ -162,12 +162,20 @@ __global__ void k_w4_pack(const uint32_t* __restrict__ qw, const uint8_t* __rest
         uint32_t word = 0;
 #pragma unroll
         for (int slot = 0; slot < 8; ++slot) {
-            int prow = st * 32 + tt * 16 + g + (((slot >> 1) & 1) ? 8 : 0);
+            int prow, k, shift;
+            if (variant == kW4VariantInt) {
+                prow = st * 32 + tt * 16 + g + ((slot & 1) ? 8 : 0);
+                k = gi * kW4GroupK + w4i_phys_k(t, j >> 1, j & 1, slot >> 1);
+                shift = 4 * slot;
+            } else {
+                prow = st * 32 + tt * 16 + g + (((slot >> 1) & 1) ? 8 : 0);
+                k = gi * kW4GroupK + w4_phys_k(t, j, slot >> 2, slot & 1);
+                shift = w4_slot_shift(slot);
+            }
             int srow = row_map ? row_map[prow] : prow;
-            int k = gi * kW4GroupK + w4_phys_k(t, j, slot >> 2, slot & 1);
             uint32_t src = qw[(size_t)srow * K8 + (k >> 3)];
             uint32_t q = (src >> km_nibble_shift(k & 7)) & 0xFu;
-            word |= q << w4_slot_shift(slot);
+            word |= q << shift;
         }
         reinterpret_cast<uint32_t*>(blk)[idx] = word;
     }
@@ -186,7 +194,7 @@ __global__ void k_w4_pack(const uint32_t* __restrict__ qw, const uint8_t* __rest
 }
 
 __global__ void k_w4_unpack(const uint8_t* __restrict__ packed, uint32_t* __restrict__ qw,
-                            uint8_t* __restrict__ qz, __half* __restrict__ sc, int N, int K) {
+                            uint8_t* __restrict__ qz, __half* __restrict__ sc, int N, int K, int variant) {
     const int G = K / kW4GroupK;
     const int K8 = K / 8;
     const int st = blockIdx.x, gi = blockIdx.y;
@@ -199,15 +207,24 @@ __global__ void k_w4_unpack(const uint8_t* __restrict__ packed, uint32_t* __rest
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
             int kin = kw * 8 + kk;                 // k within the 128-group
-            // invert w4_phys_k: kin = (u/8)*32 + t*8 + (u%8)
-            int t = (kin >> 3) & 3;
-            int u = ((kin >> 5) << 3) | (kin & 7);
-            int j = u >> 2, r = (u >> 1) & 1, e = u & 1;
-            int slot = (r << 2) | (up << 1) | e;
+            int t, j, shift;
+            if (variant == kW4VariantInt) {
+                // kin = t*32 + js*8 + p*4 + i ; word index j = 2*js + p ; nibble = 2*i + up
+                t = kin >> 5;
+                j = (((kin >> 3) & 3) << 1) | ((kin >> 2) & 1);
+                shift = 4 * (((kin & 3) << 1) | up);
+            } else {
+                // invert w4_phys_k: kin = (u/8)*32 + t*8 + (u%8)
+                t = (kin >> 3) & 3;
+                int u = ((kin >> 5) << 3) | (kin & 7);
+                j = u >> 2;
+                int r = (u >> 1) & 1, e = u & 1;
+                shift = w4_slot_shift((r << 2) | (up << 1) | e);
+            }
             int lane = g * 4 + t;
             int hh = j >> 2, jj = j & 3;
             uint32_t word = reinterpret_cast<const uint32_t*>(blk)[((tt * 2 + hh) * 32 + lane) * 4 + jj];
-            uint32_t q = (word >> w4_slot_shift(slot)) & 0xFu;
+            uint32_t q = (word >> shift) & 0xFu;
             out |= q << km_nibble_shift(kk);
         }
         qw[(size_t)(st * 32 + rr) * K8 + gi * 16 + kw] = out;
@@ -314,27 +331,40 @@ extern "C" size_t zl_w4_packed_bytes(int N, int K, int group_size) {
     return (size_t)(N / 32) * (K / kW4GroupK) * kW4BlockBytes;
 }
 
-extern "C" int zl_w4_pack(const uint32_t* qweight_km, const uint8_t* qzeros_km, const void* scales_km,
-                          const int32_t* row_map, void* packed, int N, int K, int group_size, int sym,
-                          zl_stream_t stream) {
+extern "C" int zl_w4_pack_v(const uint32_t* qweight_km, const uint8_t* qzeros_km, const void* scales_km,
+                            const int32_t* row_map, void* packed, int N, int K, int group_size, int sym, int variant,
+                            zl_stream_t stream) {
     ZL_CHECK_ARG(qweight_km && scales_km && packed && N > 0 && K > 0);
     ZL_CHECK_ARG(sym || qzeros_km);
     ZL_CHECK_SUPPORTED(group_size == kW4GroupK);
     ZL_CHECK_SUPPORTED(N % 32 == 0 && K % kW4GroupK == 0);
     dim3 grid(N / 32, K / kW4GroupK);
+    ZL_CHECK_ARG(variant == kW4VariantHalf || variant == kW4VariantInt);
     k_w4_pack<<<grid, 256, 0, stream>>>(qweight_km, qzeros_km, (const __half*)scales_km, row_map,
-                                        (uint8_t*)packed, N, K, sym);
+                                        (uint8_t*)packed, N, K, sym, variant);
+    ZL_CHECK_LAUNCH();
+    return ZL_OK;
+}
+
+extern "C" int zl_w4_pack(const uint32_t* qweight_km, const uint8_t* qzeros_km, const void* scales_km,
+                          const int32_t* row_map, void* packed, int N, int K, int group_size, int sym,
+                          zl_stream_t stream) {
+    return zl_w4_pack_v(qweight_km, qzeros_km, scales_km, row_map, packed, N, K, group_size, sym, kW4VariantHalf, stream);
+}
+
+extern "C" int zl_w4_unpack_v(const void* packed, uint32_t* qweight_km, uint8_t* qzeros_km, void* scales_km,
+                              int N, int K, int group_size, int variant, zl_stream_t stream) {
+    ZL_CHECK_ARG(packed && qweight_km && qzeros_km && scales_km && N > 0 && K > 0);
+    ZL_CHECK_SUPPORTED(group_size == kW4GroupK && N % 32 == 0 && K % kW4GroupK == 0);
+    dim3 grid(N / 32, K / kW4GroupK);
+    ZL_CHECK_ARG(variant == kW4VariantHalf || variant == kW4VariantInt);
+    k_w4_unpack<<<grid, 256, 0, stream>>>((const uint8_t*)packed, qweight_km, qzeros_km, (__half*)scales_km, N,
+                                          K, variant);
     ZL_CHECK_LAUNCH();
     return ZL_OK;
 }
 
 extern "C" int zl_w4_unpack(const void* packed, uint32_t* qweight_km, uint8_t* qzeros_km, void* scales_km,
                             int N, int K, int group_size, zl_stream_t stream) {
-    ZL_CHECK_ARG(packed && qweight_km && qzeros_km && scales_km && N > 0 && K > 0);
-    ZL_CHECK_SUPPORTED(group_size == kW4GroupK && N % 32 == 0 && K % kW4GroupK == 0);
-    dim3 grid(N / 32, K / kW4GroupK);
-    k_w4_unpack<<<grid, 256, 0, stream>>>((const uint8_t*)packed, qweight_km, qzeros_km, (__half*)scales_km, N,
-                                          K);
-    ZL_CHECK_LAUNCH();
-    return ZL_OK;
+    return zl_w4_unpack_v(packed, qweight_km, qzeros_km, scales_km, N, K, group_size, kW4VariantHalf, stream);
 }

@@ -22,7 +22,8 @@ struct Staged {
 };
 
 struct W4Lin {
-    void* packed = nullptr;
+    void* packed = nullptr;     // ZLW4  (fp16 HMMA kernels) -- only kept when some batch size needs it
+    void* packed_i = nullptr;   // ZLW4I (exact-integer IMMA kernel, small M)
     void* bias = nullptr;
     int N = 0, K = 0;
 };
@@ -204,8 +205,17 @@ int build_w4(zl_llama* m, const std::vector<std::string>& prefixes, const std::v
     }
     const size_t pbytes = zl_w4_packed_bytes(N, K, m->cfg.group_size);
     ZL_CHECK_SUPPORTED(pbytes > 0);
-    RCHECK(dmalloc(&out->packed, pbytes));
-    RCHECK(zl_w4_pack(qw_km, qz_km, sc_km, row_map, out->packed, N, K, m->cfg.group_size, m->cfg.sym, m->stream));
+    // the integer kernel serves every batch size whose staged activations fit shared memory; the fp16-MMA
+    // layout is only materialised when the configured max_batch needs it
+    const bool need_half = !zl_w4_int_kernel_fits(m->cfg.max_batch, N, K) || getenv("ZL_W4_FORCE_HALF");
+    RCHECK(dmalloc(&out->packed_i, pbytes));
+    RCHECK(zl_w4_pack_v(qw_km, qz_km, sc_km, row_map, out->packed_i, N, K, m->cfg.group_size, m->cfg.sym, 1,
+                        m->stream));
+    if (need_half) {
+        RCHECK(dmalloc(&out->packed, pbytes));
+        RCHECK(zl_w4_pack_v(qw_km, qz_km, sc_km, row_map, out->packed, N, K, m->cfg.group_size, m->cfg.sym, 0,
+                            m->stream));
+    }
     if (any_bias && !swiglu) {
         RCHECK(dmalloc(&out->bias, (size_t)N * 2));
         ZL_CHECK_CUDA(cudaMemsetAsync(out->bias, 0, (size_t)N * 2, m->stream));
@@ -385,7 +395,13 @@ int w4_gemm(zl_llama* m, const void* x, int ldx, const W4Lin& w, const void* res
     zl_w4_fused_args_t a = {};
     a.x = x;
     a.ldx = ldx;
-    a.packed = w.packed;
+    const bool use_int = w.packed_i && !getenv("ZL_W4_FORCE_HALF") && zl_w4_int_kernel_fits(B, w.N, w.K);
+    a.packed = use_int ? w.packed_i : w.packed;
+    a.variant = use_int ? 1 : 0;
+    if (!a.packed) {
+        zl_set_last_error(__FILE__, __LINE__, "no packed weight variant for this batch size");
+        return ZL_ERR_STATE;
+    }
     a.bias = w.bias;
     a.residual = residual;
     a.y = y;
@@ -574,7 +590,7 @@ extern "C" void zl_llama_destroy(zl_llama_t* m) {
     for (auto& s : m->staged) cudaFree(s.second.ptr);
     for (auto& L : m->layers) {
         for (void* p : {L.ln_attn, L.ln_ff, L.q_qkv.packed, L.q_qkv.bias, L.q_o.packed, L.q_o.bias, L.q_gu.packed,
-                        L.q_down.packed, L.q_down.bias, L.d_qkv.w, L.d_qkv.bias, L.d_o.w, L.d_o.bias, L.d_gu.w,
+                        L.q_down.packed, L.q_down.bias, L.q_qkv.packed_i, L.q_o.packed_i, L.q_gu.packed_i, L.q_down.packed_i, L.d_qkv.w, L.d_qkv.bias, L.d_o.w, L.d_o.bias, L.d_gu.w,
                         L.d_gu.bias, L.d_down.w, L.d_down.bias, L.kbuf, L.vbuf, (void*)L.k_addrs, (void*)L.v_addrs})
             if (p) cudaFree(p);
     }
@@ -750,6 +766,7 @@ extern "C" int zl_llama_bench_gemms(zl_llama_t* m, int B, int iters, float* ms, 
     const int D = c.dim_model, d = c.dim_head, dt = c.dtype, pdl = c.use_pdl;
     const bool w4 = c.quant_type == 5 || c.quant_type == 6;
     cudaStream_t st = m->stream;
+    (void)pdl;
     cudaEvent_t e0, e1;
     ZL_CHECK_CUDA(cudaEventCreate(&e0));
     ZL_CHECK_CUDA(cudaEventCreate(&e1));
@@ -760,14 +777,10 @@ extern "C" int zl_llama_bench_gemms(zl_llama_t* m, int B, int iters, float* ms, 
         for (int l = 0; l < c.num_layers; ++l) {
             Layer& L = m->layers[l];
             if (w4) {
-                RCHECK(zl_w4a16_gemm(m->xn, D, L.q_qkv.packed, L.q_qkv.bias, nullptr, m->qkv, B, L.q_qkv.N, D,
-                                     c.group_size, ZL_EPI_NONE, pdl, st));
-                RCHECK(zl_w4a16_gemm(m->ao, m->hq * d, L.q_o.packed, L.q_o.bias, m->pend, m->pend, B, D, m->hq * d,
-                                     c.group_size, ZL_EPI_RESIDUAL, pdl, st));
-                RCHECK(zl_w4a16_gemm(m->xn, D, L.q_gu.packed, nullptr, nullptr, m->act, B, L.q_gu.N, D,
-                                     c.group_size, ZL_EPI_SWIGLU, pdl, st));
-                RCHECK(zl_w4a16_gemm(m->act, m->ff, L.q_down.packed, L.q_down.bias, m->pend, m->pend, B, D, m->ff,
-                                     c.group_size, ZL_EPI_RESIDUAL, pdl, st));
+                RCHECK(w4_gemm(m, m->xn, D, L.q_qkv, nullptr, m->qkv, B, ZL_EPI_NONE, nullptr, nullptr));
+                RCHECK(w4_gemm(m, m->ao, m->hq * d, L.q_o, m->pend, m->pend, B, ZL_EPI_RESIDUAL, nullptr, nullptr));
+                RCHECK(w4_gemm(m, m->xn, D, L.q_gu, nullptr, m->act, B, ZL_EPI_SWIGLU, nullptr, nullptr));
+                RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, m->pend, m->pend, B, ZL_EPI_RESIDUAL, nullptr, nullptr));
                 if (it == 0) {
                     nbytes += (double)zl_w4_packed_bytes(L.q_qkv.N, D, c.group_size) +
                               (double)zl_w4_packed_bytes(D, m->hq * d, c.group_size) +

@@ -41,4 +41,13 @@ __host__ __device__ __forceinline__ int w4_phys_k(int t, int j, int r, int e) {
     return (u >> 3) * 32 + t * 8 + (u & 7);
 }
 
+// ---- ZLW4I: same 2128-byte block, nibble order for the exact-integer kernel (IMMA m16n8k32) -------------
+//   word wi = 2*j + p of lane (g,t) (j = MMA k-step 0..3, p = register pair 0/1) holds, for byte i = 0..3:
+//     nibble 2i   = W[row g  ][k = t*32 + j*8 + p*4 + i]        -> A reg a_{2p}   = w & 0x0f0f0f0f
+//     nibble 2i+1 = W[row g+8][same k]                           -> A reg a_{2p+1} = w & 0xf0f0f0f0 (value * 16)
+//   i.e. k is in NATURAL order inside the group, so the matching B fragments (int8 activation pieces) of a
+//   lane are 32 contiguous bytes.  Meta (scales / zeros) as in ZLW4.
+enum { kW4VariantHalf = 0, kW4VariantInt = 1 };
+__host__ __device__ __forceinline__ int w4i_phys_k(int t, int j, int pp, int i) { return t * 32 + j * 8 + pp * 4 + i; }
+
 }  // namespace zl

@@ -26,9 +26,14 @@ struct W4Params {
     __half* const* k_addrs;
     __half* const* v_addrs;
     int num_heads, num_kv_heads, dim_head;
+    int dbg;   // ZL_W4_DEBUG: 1 = skip dequant/MMA (pure weight-stream probe; results are garbage)
 };
 
 cudaError_t launch_w4_v2(const W4Params& p, bool pdl, cudaStream_t stream);
 cudaError_t prepare_w4_v2();
+// exact-integer kernel on the ZLW4I layout; false = staged activations do not fit shared memory
+bool launch_w4_v3(const W4Params& p, bool pdl, cudaStream_t stream, cudaError_t* err);
+bool w4_v3_fits(int mc, int N, int K);
+cudaError_t prepare_w4_v3();
 
 }  // namespace zl

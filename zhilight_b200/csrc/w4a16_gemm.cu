@@ -248,6 +248,7 @@ extern "C" int zl_prepare(void) {
     ZL_CHECK_CUDA(cudaFuncSetAttribute(k_w4a16_mma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kW4SmemBytes));
     ZL_CHECK_CUDA(cudaFuncSetAttribute(k_w4a16_mma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kW4SmemBytes));
     ZL_CHECK_CUDA(prepare_w4_v2());
+    ZL_CHECK_CUDA(prepare_w4_v3());
     return ZL_OK;
 }
 
@@ -278,6 +279,12 @@ __global__ void k_gather_16(const uint16_t* __restrict__ src, const int32_t* __r
 }
 }  // namespace zl
 
+extern "C" int zl_w4_int_kernel_fits(int M, int N, int K) {
+    if (M <= 0 || N <= 0 || K <= 0 || N % 32 || K % kW4GroupK) return 0;
+    const int mc = M < 32 ? M : 32;
+    return w4_v3_fits(mc, N, K) ? 1 : 0;
+}
+
 extern "C" int zl_qkv_rope_row_map(int32_t* row_map, int n_heads_total, int dim_head, zl_stream_t stream) {
     ZL_CHECK_ARG(row_map && n_heads_total > 0 && dim_head > 0);
     ZL_CHECK_SUPPORTED(dim_head % 32 == 0);
@@ -307,6 +314,7 @@ extern "C" int zl_w4a16_gemm_fused(const zl_w4_fused_args_t* a, zl_stream_t stre
     ZL_CHECK_ARG(a->ldx >= a->K && a->ldx % 8 == 0);
     ZL_CHECK_ARG((reinterpret_cast<uintptr_t>(a->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->packed) & 15) == 0);
     ZL_CHECK_ARG(a->epilogue >= ZL_EPI_NONE && a->epilogue <= ZL_EPI_QKV_ROPE);
+    ZL_CHECK_ARG(a->variant == kW4VariantHalf || a->variant == kW4VariantInt);
     ZL_CHECK_ARG(a->epilogue != ZL_EPI_RESIDUAL || a->residual != nullptr);
     ZL_CHECK_ARG(a->epilogue == ZL_EPI_QKV_ROPE || a->y != nullptr);
     ZL_CHECK_ARG(a->ln_weight == nullptr || (reinterpret_cast<uintptr_t>(a->ln_weight) & 15) == 0);
@@ -341,7 +349,22 @@ extern "C" int zl_w4a16_gemm_fused(const zl_w4_fused_args_t* a, zl_stream_t stre
         p.num_heads = a->num_heads;
         p.num_kv_heads = a->num_kv_heads;
         p.dim_head = a->dim_head;
-        ZL_CHECK_CUDA(launch_w4_v2(p, a->pdl != 0 && m0 == 0, stream));
+        {
+            static int dbg = -1;
+            if (dbg < 0) {
+                const char* e = getenv("ZL_W4_DEBUG");
+                dbg = e ? atoi(e) : 0;
+            }
+            p.dbg = dbg;
+        }
+        if (a->variant == kW4VariantInt) {
+            cudaError_t ce = cudaSuccess;
+            const bool ok = launch_w4_v3(p, a->pdl != 0 && m0 == 0, stream, &ce);
+            ZL_CHECK_SUPPORTED(ok && "ZLW4I kernel: staged activations do not fit shared memory (use variant 0)");
+            ZL_CHECK_CUDA(ce);
+        } else {
+            ZL_CHECK_CUDA(launch_w4_v2(p, a->pdl != 0 && m0 == 0, stream));
+        }
     }
     return ZL_OK;
 }

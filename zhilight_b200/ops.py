@@ -104,7 +104,7 @@ def gptq_dequant_k_major(qweight_km, qzeros_km, scales_km):
     return out
 
 
-def w4_pack(qweight_km, qzeros_km, scales_km, group_size=128, sym=False, row_map=None):
+def w4_pack(qweight_km, qzeros_km, scales_km, group_size=128, sym=False, row_map=None, variant=0):
     n_src, k8 = qweight_km.shape
     n = n_src if row_map is None else row_map.numel()
     k = k8 * 8
@@ -112,17 +112,17 @@ def w4_pack(qweight_km, qzeros_km, scales_km, group_size=128, sym=False, row_map
     if nbytes == 0:
         raise _lib.ZLError(-2, "unsupported ZLW4 shape N=%d K=%d group=%d" % (n, k, group_size))
     packed = torch.empty(nbytes, dtype=torch.uint8, device=qweight_km.device)
-    _lib.call("zl_w4_pack", _p(qweight_km), _p(qzeros_km), _p(scales_km), _p(row_map), _p(packed), n, k, group_size,
-              int(sym), _stream())
+    _lib.call("zl_w4_pack_v", _p(qweight_km), _p(qzeros_km), _p(scales_km), _p(row_map), _p(packed), n, k, group_size,
+              int(sym), int(variant), _stream())
     return packed
 
 
-def w4_unpack(packed, n, k, group_size=128):
+def w4_unpack(packed, n, k, group_size=128, variant=0):
     dev = packed.device
     qw = torch.empty((n, k // 8), dtype=torch.int32, device=dev)
     qz = torch.empty((n, k // group_size), dtype=torch.uint8, device=dev)
     sc = torch.empty((n, k // group_size), dtype=torch.float16, device=dev)
-    _lib.call("zl_w4_unpack", _p(packed), _p(qw), _p(qz), _p(sc), n, k, group_size, _stream())
+    _lib.call("zl_w4_unpack_v", _p(packed), _p(qw), _p(qz), _p(sc), n, k, group_size, int(variant), _stream())
     return qw, qz, sc
 
 
@@ -163,7 +163,7 @@ def gather_rows_16(src, row_map):
 
 
 def w4a16_gemm_fused(x, packed, n, k, group_size=128, bias=None, residual=None, epilogue=EPI_NONE, pdl=False, out=None,
-                     ln_weight=None, eps=1e-5, rope=None):
+                     ln_weight=None, eps=1e-5, rope=None, variant=0):
     """zl_w4a16_gemm_fused.  rope = dict(cos, sin, token_batch, placement, k_bufs, v_bufs, num_heads, num_kv_heads,
     dim_head) for EPI_QKV_ROPE (returns q); bias must be in packed-row order."""
     if x.dtype != torch.float16:
@@ -173,6 +173,7 @@ def w4a16_gemm_fused(x, packed, n, k, group_size=128, bias=None, residual=None, 
     a.x, a.ldx, a.packed, a.bias, a.residual = x.data_ptr(), x.stride(0), packed.data_ptr(), _dp(bias), _dp(residual)
     a.M, a.N, a.K, a.group_size, a.epilogue, a.pdl = m, n, k, group_size, epilogue, int(pdl)
     a.ln_weight, a.eps = _dp(ln_weight), eps
+    a.variant = int(variant)
     keep = []
     if epilogue == EPI_QKV_ROPE:
         r = rope
