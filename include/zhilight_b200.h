@@ -121,11 +121,14 @@ typedef struct zl_w4_fused_args {
     const float* cos; const float* sin; void* q_out;
     const int32_t* token_batch; const int32_t* placement; void* const* k_addrs; void* const* v_addrs;
     int num_heads, num_kv_heads, dim_head;
+    const void* prefetch_ptr; size_t prefetch_bytes; /* next kernel's weights: pulled into L2 as this one drains (may be NULL) */
     int variant; /* layout of `packed`: 0 ZLW4, 1 ZLW4I (integer kernel; needs the staged activations to fit smem) */
 } zl_w4_fused_args_t;
 int zl_w4a16_gemm_fused(const zl_w4_fused_args_t* args, zl_stream_t stream);
 /* 1 if the exact-integer kernel (variant 1) can run this shape: its staged activations must fit shared memory. */
 int zl_w4_int_kernel_fits(int M, int N, int K);
+/* debug: device buffer of grid*16 uint64 globaltimer samples written by the integer kernel (NULL = off). */
+int zl_w4_set_trace(void* buf);
 /* row_map (n_heads_total*dim_head) for zl_w4_pack so that RoPE partners (c, c+d/2) share an MMA tile. */
 int zl_qkv_rope_row_map(int32_t* row_map, int n_heads_total, int dim_head, zl_stream_t stream);
 /* dst[i] = src[map[i]] for 16-bit elements (bias permutation to packed-row order). */

@@ -49,6 +49,7 @@ class W4FusedArgs(ctypes.Structure):
         ("token_batch", ctypes.c_void_p), ("placement", ctypes.c_void_p), ("k_addrs", ctypes.c_void_p),
         ("v_addrs", ctypes.c_void_p),
         ("num_heads", ctypes.c_int), ("num_kv_heads", ctypes.c_int), ("dim_head", ctypes.c_int),
+        ("prefetch_ptr", ctypes.c_void_p), ("prefetch_bytes", ctypes.c_size_t),
         ("variant", ctypes.c_int),
     ]
 

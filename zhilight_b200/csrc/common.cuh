@@ -115,6 +115,36 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
         : "memory");
 }
 
+// same copy, tagged evict-first in L2: a weight stream is read exactly once per step and must not push the
+// prefetched weights of the NEXT kernel (l2_prefetch below) out of the 126 MB L2
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
+                                              uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+// fire-and-forget prefetch of [p, p+bytes) into L2 (bytes % 16 == 0, p 16-B aligned)
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// each (cta, warp) of the grid prefetches its strided share of [base, base+bytes) in 4 KB pieces; call from lane 0
+__device__ __forceinline__ void l2_prefetch_share(const uint8_t* base, size_t bytes, int part, int parts) {
+    constexpr size_t kChunk = 4096;
+    const size_t n_chunks = (bytes + kChunk - 1) / kChunk;
+    for (size_t c = (size_t)part; c < n_chunks; c += (size_t)parts) {
+        const size_t off = c * kChunk;
+        const size_t len = bytes - off < kChunk ? bytes - off : kChunk;
+        l2_prefetch(base + off, (uint32_t)(len & ~(size_t)15));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // loads
 // ---------------------------------------------------------------------------------------------
@@ -217,6 +247,12 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
+}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }   // activation.cuh:12-14

@@ -389,8 +389,18 @@ int alloc_runtime(zl_llama* m) {
 // The decode-step kernel chain (captured into a graph by run_step).
 // cfg.fuse: 0 = one kernel per reference operator; 1 = RMSNorm folded into the following W4 GEMM;
 //           2 = additionally qkv split + RoPE + KV append folded into the qkv GEMM epilogue.
+// cap of the L2 prefetch a kernel issues for its successor (bytes); ZL_L2_PREFETCH_MB overrides, 0 disables
+static size_t prefetch_cap() {
+    static long v = -1;
+    if (v < 0) {
+        const char* e = getenv("ZL_L2_PREFETCH_MB");
+        v = e ? atol(e) : 24;
+    }
+    return (size_t)v << 20;
+}
+
 int w4_gemm(zl_llama* m, const void* x, int ldx, const W4Lin& w, const void* residual, void* y, int B, int epi,
-            const void* ln_w, const Layer* rope_layer) {
+            const void* ln_w, const Layer* rope_layer, const W4Lin* next = nullptr) {
     const auto& c = m->cfg;
     zl_w4_fused_args_t a = {};
     a.x = x;
@@ -398,6 +408,12 @@ int w4_gemm(zl_llama* m, const void* x, int ldx, const W4Lin& w, const void* res
     const bool use_int = w.packed_i && !getenv("ZL_W4_FORCE_HALF") && zl_w4_int_kernel_fits(B, w.N, w.K);
     a.packed = use_int ? w.packed_i : w.packed;
     a.variant = use_int ? 1 : 0;
+    if (next && prefetch_cap() > 0) {
+        const bool next_int = next->packed_i && !getenv("ZL_W4_FORCE_HALF") && zl_w4_int_kernel_fits(B, next->N, next->K);
+        a.prefetch_ptr = next_int ? next->packed_i : next->packed;
+        const size_t nb = zl_w4_packed_bytes(next->N, next->K, c.group_size);
+        a.prefetch_bytes = nb < prefetch_cap() ? nb : prefetch_cap();
+    }
     if (!a.packed) {
         zl_set_last_error(__FILE__, __LINE__, "no packed weight variant for this batch size");
         return ZL_ERR_STATE;
@@ -465,9 +481,9 @@ int enqueue_step(zl_llama* m, int B, int len_bucket) {
             }
             if (skip & 2) {
             } else if (c.fuse >= 2) {
-                RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, nullptr, B, ZL_EPI_QKV_ROPE, lnw, &L));
+                RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, nullptr, B, ZL_EPI_QKV_ROPE, lnw, &L, &L.q_o));
             } else {
-                RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, m->qkv, B, ZL_EPI_NONE, lnw, nullptr));
+                RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, m->qkv, B, ZL_EPI_NONE, lnw, nullptr, &L.q_o));
             }
         } else {
             // residual of the previous layer's FFN is folded into this norm (block.cpp:139-141 + 131)
@@ -484,7 +500,7 @@ int enqueue_step(zl_llama* m, int B, int len_bucket) {
                                        m->hq, m->hkv, d, 1, m->attn_ws, m->attn_ws_bytes, dt, pdl, st));
         if (w4) {
             if (!(skip & 4))
-                RCHECK(w4_gemm(m, m->ao, m->hq * d, L.q_o, m->h, m->h, B, ZL_EPI_RESIDUAL, nullptr, nullptr));
+                RCHECK(w4_gemm(m, m->ao, m->hq * d, L.q_o, m->h, m->h, B, ZL_EPI_RESIDUAL, nullptr, nullptr, &L.q_gu));
             const void* xin = m->xn;
             const void* lnw = nullptr;
             if (c.fuse >= 1) {
@@ -493,9 +509,10 @@ int enqueue_step(zl_llama* m, int B, int len_bucket) {
             } else {
                 RCHECK(zl_rmsnorm(m->h, L.ln_ff, m->xn, B, D, c.eps, 1.f, dt, pdl, st));
             }
-            if (!(skip & 8)) RCHECK(w4_gemm(m, xin, D, L.q_gu, nullptr, m->act, B, ZL_EPI_SWIGLU, lnw, nullptr));
+            if (!(skip & 8)) RCHECK(w4_gemm(m, xin, D, L.q_gu, nullptr, m->act, B, ZL_EPI_SWIGLU, lnw, nullptr, &L.q_down));
             if (!(skip & 16))
-                RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, m->h, m->h, B, ZL_EPI_RESIDUAL, nullptr, nullptr));
+                RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, m->h, m->h, B, ZL_EPI_RESIDUAL, nullptr, nullptr,
+                               l + 1 < c.num_layers ? &m->layers[l + 1].q_qkv : nullptr));
         } else {
             RCHECK(zl_dense_gemm_skinny(m->ao, m->hq * d, L.d_o.w, L.d_o.bias, m->pend, B, D, m->hq * d, dt, dt, pdl,
                                         st));

@@ -26,6 +26,10 @@ struct W4Params {
     __half* const* k_addrs;
     __half* const* v_addrs;
     int num_heads, num_kv_heads, dim_head;
+    // weights of the NEXT kernel in the chain: prefetched into L2 when this CTA runs out of work (may be null)
+    const uint8_t* pf_ptr;
+    unsigned long long pf_bytes;
+    unsigned long long* trace;   // debug: per-CTA globaltimer samples [grid][16] (zl_w4_set_trace)
     int dbg;   // ZL_W4_DEBUG: 1 = skip dequant/MMA (pure weight-stream probe; results are garbage)
 };
 

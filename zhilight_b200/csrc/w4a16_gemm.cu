@@ -279,6 +279,12 @@ __global__ void k_gather_16(const uint16_t* __restrict__ src, const int32_t* __r
 }
 }  // namespace zl
 
+static unsigned long long* g_w4_trace = nullptr;
+extern "C" int zl_w4_set_trace(void* buf) {
+    g_w4_trace = static_cast<unsigned long long*>(buf);
+    return ZL_OK;
+}
+
 extern "C" int zl_w4_int_kernel_fits(int M, int N, int K) {
     if (M <= 0 || N <= 0 || K <= 0 || N % 32 || K % kW4GroupK) return 0;
     const int mc = M < 32 ? M : 32;
@@ -357,6 +363,9 @@ extern "C" int zl_w4a16_gemm_fused(const zl_w4_fused_args_t* a, zl_stream_t stre
             }
             p.dbg = dbg;
         }
+        p.trace = g_w4_trace;
+        p.pf_ptr = static_cast<const uint8_t*>(a->prefetch_ptr);
+        p.pf_bytes = a->prefetch_bytes;
         if (a->variant == kW4VariantInt) {
             cudaError_t ce = cudaSuccess;
             const bool ok = launch_w4_v3(p, a->pdl != 0 && m0 == 0, stream, &ce);

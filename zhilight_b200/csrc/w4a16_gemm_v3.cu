@@ -19,6 +19,8 @@
 #include "w4_layout.cuh"
 #include "w4_params.h"
 
+#include <cstdlib>
+
 namespace zl {
 
 __device__ __forceinline__ void imma_u8s8(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -34,120 +36,174 @@ __device__ __forceinline__ void imma_u8u8(int (&d)[4], const uint32_t (&a)[4], u
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// per-warp staging area: for every token row the warp's k-slice as hi / lo bytes, plus (sum m, 2^e) per group
-template <int NT, int WARPS, int STAGES>
+// Shared-memory plan.  A CTA holds SUBS independent "sub-CTAs" of WARPS warps; each sub-CTA walks its own stream
+// of 32-row tiles (k split over its WARPS warps, private bulk-TMA rings, own named barrier for the split-k
+// reduction), while the integer decomposition of the activations is staged ONCE per CTA by all warps together:
+//   wide : SUBS=2 x 8 warps, 5-stage rings  (N/32 > #SMs: qkv, gate/up)  -- two tile pipelines per SM
+//   tall : SUBS=1 x 16 warps, 4-stage rings (N/32 <= #SMs: o_proj, down) -- k split 16 ways
+template <int NT, int WARPS, int SUBS, int STAGES>
 struct V3Smem {
-    static constexpr int kRingBytes = WARPS * STAGES * kW4BlockBytes;
-    static constexpr int kRedBufs = (NT == 1 && WARPS == 8) ? 2 : 1;
-    static constexpr int kRedFloats = WARPS * NT * 8 * 32;
+    static constexpr int kWarpsTotal = WARPS * SUBS;
+    static constexpr int kRingBytes = kWarpsTotal * STAGES * kW4BlockBytes;
+    static constexpr int kRedBufs = (NT == 1) ? 2 : 1;
+    static constexpr int kRedFloats = WARPS * NT * 8 * 32;                 // per sub-CTA, per buffer
     static constexpr int kBarOff = kRingBytes;
-    static constexpr int kRedOff = kBarOff + WARPS * STAGES * 8;
-    static constexpr int kSsOff = kRedOff + kRedBufs * kRedFloats * 4;   // [warps][NT*8]
-    static constexpr int kRstdOff = kSsOff + WARPS * NT * 8 * 4;         // [NT*8]
+    static constexpr int kRedOff = kBarOff + kWarpsTotal * STAGES * 8;
+    static constexpr int kSsOff = kRedOff + SUBS * kRedBufs * kRedFloats * 4;   // [warps total][NT*8]
+    static constexpr int kRstdOff = kSsOff + kWarpsTotal * NT * 8 * 4;          // [NT*8]
     static constexpr int kXOff = (kRstdOff + NT * 8 * 4 + 127) & ~127;
     static constexpr int kBytes = kXOff;
 };
-// bytes of the staging area for one warp: mc rows x (hi + lo) + group table
-__host__ __device__ inline int v3_row_bytes(int ng_max) { return ng_max * 128 + 16; }   // +16: conflict-free LDS.128
-__host__ __device__ inline int v3_warp_bytes(int mc, int ng_max) {
-    return 2 * mc * v3_row_bytes(ng_max) + ng_max * mc * 8;
+// staged activations (whole K): mc rows of hi bytes, mc rows of lo bytes, then the group table
+__host__ __device__ inline int v3_row_bytes(int K) { return K + 16; }   // +16: conflict-free LDS.128 across tokens
+__host__ __device__ inline int v3_stage_bytes(int mc, int K) {
+    return 2 * mc * v3_row_bytes(K) + (K / kW4GroupK) * mc * 8;
 }
 
-template <int NT, bool NORM, int WARPS, int STAGES>
-__global__ void __launch_bounds__(WARPS * 32, ((NT <= 2 && WARPS == 8) ? 2 : 1)) k_w4a16_v3(const W4Params p) {
-    using S = V3Smem<NT, WARPS, STAGES>;
+__device__ __forceinline__ void sub_barrier(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int NT, bool NORM, int WARPS, int SUBS, int STAGES>
+__global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Params p) {
+    using S = V3Smem<NT, WARPS, SUBS, STAGES>;
+    constexpr int WT = WARPS * SUBS;
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = warp / WARPS, wl = warp % WARPS;   // sub-CTA, warp within it
+    const int stid = threadIdx.x - sub * (WARPS * 32);  // thread index within the sub-CTA
     const int g = lane >> 2, t = lane & 3;
     const int G = p.K / kW4GroupK;
-    const int g_begin = (warp * G) / WARPS;
-    const int g_end = ((warp + 1) * G) / WARPS;
+    const int g_begin = (wl * G) / WARPS;
+    const int g_end = ((wl + 1) * G) / WARPS;
     const int ng = g_end - g_begin;
-    const int ng_max = (G + WARPS - 1) / WARPS;
     const int n_tiles = p.N / 32;
-    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int tile0 = (int)blockIdx.x * SUBS + sub;
+    const int tile_stride = (int)gridDim.x * SUBS;
+    const int my_tiles = tile0 < n_tiles ? (n_tiles - tile0 + tile_stride - 1) / tile_stride : 0;
     const int total = my_tiles * ng;
 
     uint8_t* ring = smem + warp * (STAGES * kW4BlockBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBarOff) + warp * STAGES;
-    float* red = reinterpret_cast<float*>(smem + S::kRedOff);
+    float* red = reinterpret_cast<float*>(smem + S::kRedOff) + sub * (S::kRedBufs * S::kRedFloats);
     float* s_ss = reinterpret_cast<float*>(smem + S::kSsOff);
     float* s_rstd = reinterpret_cast<float*>(smem + S::kRstdOff);
-    const int row_b = v3_row_bytes(ng_max);
-    uint8_t* xw_hi = smem + S::kXOff + warp * v3_warp_bytes(p.mc, ng_max);   // [tok][row_b]
-    uint8_t* xw_lo = xw_hi + p.mc * row_b;                                   // [tok][row_b]
-    int2* xw_tab = reinterpret_cast<int2*>(xw_lo + p.mc * row_b);            // [group][tok] {sum m, bits of 2^e}
+    const int row_b = v3_row_bytes(p.K);
+    uint8_t* xs_hi = smem + S::kXOff;                                    // [tok][row_b]
+    uint8_t* xs_lo = xs_hi + p.mc * row_b;                               // [tok][row_b]
+    int2* xs_tab = reinterpret_cast<int2*>(xs_lo + p.mc * row_b);        // [group][tok] {sum m, bits of 2^e}
 
-    auto item_src = [&](int it) -> const uint8_t* {
-        const int tile = (int)blockIdx.x + (it / ng) * (int)gridDim.x;
-        const int gi = g_begin + it % ng;
-        return p.packed + ((size_t)tile * G + gi) * kW4BlockBytes;
+    // producer cursor (lane 0): next ring item = (tile p_tile, group p_g) -> slot p_slot
+    int p_issued = 0, p_tile = tile0, p_g = 0, p_slot = 0;
+    const uint64_t pol = l2_evict_first_policy();
+    auto issue_next = [&]() {
+        mbar_expect_tx(&bars[p_slot], kW4BlockBytes);
+        bulk_g2s_hint(ring + p_slot * kW4BlockBytes, p.packed + ((size_t)p_tile * G + g_begin + p_g) * kW4BlockBytes,
+                      kW4BlockBytes, &bars[p_slot], pol);
+        ++p_issued;
+        if (++p_slot == STAGES) p_slot = 0;
+        if (++p_g == ng) {
+            p_g = 0;
+            p_tile += tile_stride;
+        }
     };
 
+    unsigned long long* tr = p.trace ? p.trace + (size_t)blockIdx.x * 16 : nullptr;
+    int tr_n = 0;
+    auto stamp = [&]() {
+        if (tr && threadIdx.x == 0 && tr_n < 16) tr[tr_n++] = globaltimer_ns();
+    };
+    stamp();
     pdl_trigger();
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
         mbar_fence_init();
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) {
-            if (s < total) {
-                mbar_expect_tx(&bars[s], kW4BlockBytes);
-                bulk_g2s(ring + s * kW4BlockBytes, item_src(s), kW4BlockBytes, &bars[s]);
-            }
+        for (int s = 0; s < STAGES; ++s)
+            if (s < total) issue_next();
+    }
+    // staging assignment: group gi -> warp gi % WT.  RMSNorm weights are constants: fetch them before the wait.
+    constexpr int kMaxNg = 8;   // groups per warp kept in registers during staging (K <= 8*WT*128)
+    uint2 lnw[kMaxNg];
+    if (NORM) {
+#pragma unroll
+        for (int gl = 0; gl < kMaxNg; ++gl) {
+            const int gi = warp + gl * WT;
+            if (gi < G) lnw[gl] = *reinterpret_cast<const uint2*>(p.ln_w + gi * kW4GroupK + lane * 4);
         }
     }
     __syncwarp();
-    pdl_wait();
+    stamp();
+    pdl_wait();   // everything above touched only constants; x / residual / KV come from predecessor kernels
+    stamp();
 
-    // ---- stage this warp's k-slice of the activations as block-floating-point integers (warp-local) ----
+    // ---- stage the activations as block-floating-point integers, once per CTA ----
     for (int tok = 0; tok < p.mc; ++tok) {
-        float sq = 0.f;
-        for (int gl = 0; gl < ng; ++gl) {
-            const int k = (g_begin + gl) * kW4GroupK + lane * 4;
-            uint2 raw = ld_cg_u2(p.x + (size_t)tok * p.ldx + k);
-            __half2 h01 = *reinterpret_cast<__half2*>(&raw.x), h23 = *reinterpret_cast<__half2*>(&raw.y);
-            if (NORM) {
-                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                sq = fmaf(f01.x, f01.x, sq);
-                sq = fmaf(f01.y, f01.y, sq);
-                sq = fmaf(f23.x, f23.x, sq);
-                sq = fmaf(f23.y, f23.y, sq);
-                const uint2 wr = *reinterpret_cast<const uint2*>(p.ln_w + k);
-                h01 = __hmul2(h01, *reinterpret_cast<const __half2*>(&wr.x));
-                h23 = __hmul2(h23, *reinterpret_cast<const __half2*>(&wr.y));
-            }
-            const float2 a = __half22float2(h01), b = __half22float2(h23);
-            float amax = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(b.x), fabsf(b.y)));
-            amax = warp_max(amax);
-            // 2^e with m = x * 2^-e in (-2^15, 2^15): e = floor(log2 amax) - 14
-            const uint32_t ex = (__float_as_uint(amax) >> 23) & 0xffu;
-            const bool zero = !(amax > 0.f) || !(amax < INFINITY) || ex < 20u;   // all-zero / non-finite / tiny group
-            const float sg = zero ? 1.0f : __uint_as_float((ex - 14u) << 23);
-            const float inv = zero ? 0.0f : __uint_as_float((254u - (ex - 14u)) << 23);
-            const int m0 = __float2int_rn(a.x * inv), m1 = __float2int_rn(a.y * inv);
-            const int m2 = __float2int_rn(b.x * inv), m3 = __float2int_rn(b.y * inv);
-            const uint32_t lo = (uint32_t)(m0 & 255) | ((uint32_t)(m1 & 255) << 8) | ((uint32_t)(m2 & 255) << 16) |
-                                ((uint32_t)(m3 & 255) << 24);
-            const uint32_t hi = (uint32_t)((m0 >> 8) & 255) | ((uint32_t)((m1 >> 8) & 255) << 8) |
-                                ((uint32_t)((m2 >> 8) & 255) << 16) | ((uint32_t)((m3 >> 8) & 255) << 24);
-            *reinterpret_cast<uint32_t*>(xw_hi + tok * row_b + gl * 128 + lane * 4) = hi;
-            *reinterpret_cast<uint32_t*>(xw_lo + tok * row_b + gl * 128 + lane * 4) = lo;
-            int sm = m0 + m1 + m2 + m3;
+        uint2 raw[kMaxNg];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
-            if (lane == 0) xw_tab[gl * p.mc + tok] = make_int2(sm, (int)__float_as_uint(sg));
+        for (int gl = 0; gl < kMaxNg; ++gl) {
+            const int gi = warp + gl * WT;
+            if (gi < G) raw[gl] = ld_cg_u2(p.x + (size_t)tok * p.ldx + gi * kW4GroupK + lane * 4);
+        }
+        float sq = 0.f;
+#pragma unroll
+        for (int gl = 0; gl < kMaxNg; ++gl) {
+            const int gi = warp + gl * WT;
+            if (gi < G) {
+                __half2 h01 = *reinterpret_cast<__half2*>(&raw[gl].x), h23 = *reinterpret_cast<__half2*>(&raw[gl].y);
+                if (NORM) {
+                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                    sq = fmaf(f01.x, f01.x, sq);
+                    sq = fmaf(f01.y, f01.y, sq);
+                    sq = fmaf(f23.x, f23.x, sq);
+                    sq = fmaf(f23.y, f23.y, sq);
+                    h01 = __hmul2(h01, *reinterpret_cast<const __half2*>(&lnw[gl].x));
+                    h23 = __hmul2(h23, *reinterpret_cast<const __half2*>(&lnw[gl].y));
+                }
+                const float2 a = __half22float2(h01), b = __half22float2(h23);
+                const float amax_l = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(b.x), fabsf(b.y)));
+                // non-negative floats order like their bit patterns: one REDUX instead of a shuffle tree
+                const uint32_t amax_bits = __reduce_max_sync(0xffffffffu, __float_as_uint(amax_l));
+                // 2^e with m = x * 2^-e in (-2^15, 2^15): e = floor(log2 amax) - 14
+                const uint32_t ex = (amax_bits >> 23) & 0xffu;
+                const bool zero = ex < 20u || ex == 0xffu;   // all-zero / tiny / non-finite group -> contributes 0
+                const float sg = zero ? 1.0f : __uint_as_float((ex - 14u) << 23);
+                const float inv = zero ? 0.0f : __uint_as_float((268u - ex) << 23);
+                const int m0 = __float2int_rn(a.x * inv), m1 = __float2int_rn(a.y * inv);
+                const int m2 = __float2int_rn(b.x * inv), m3 = __float2int_rn(b.y * inv);
+                // byte 0 of each m -> lo, byte 1 -> hi (two's complement high byte == floor(m / 256)): 6 PRMTs
+                const uint32_t lo = __byte_perm(__byte_perm((uint32_t)m0, (uint32_t)m1, 0x0040),
+                                                __byte_perm((uint32_t)m2, (uint32_t)m3, 0x0040), 0x5410);
+                const uint32_t hi = __byte_perm(__byte_perm((uint32_t)m0, (uint32_t)m1, 0x0051),
+                                                __byte_perm((uint32_t)m2, (uint32_t)m3, 0x0051), 0x5410);
+                *reinterpret_cast<uint32_t*>(xs_hi + tok * row_b + gi * 128 + lane * 4) = hi;
+                *reinterpret_cast<uint32_t*>(xs_lo + tok * row_b + gi * 128 + lane * 4) = lo;
+                const int sm = __reduce_add_sync(0xffffffffu, m0 + m1 + m2 + m3);
+                if (lane == 0) xs_tab[gi * p.mc + tok] = make_int2(sm, (int)__float_as_uint(sg));
+            }
         }
         if (NORM) {
             sq = warp_sum(sq);
             if (lane == 0) s_ss[warp * (NT * 8) + tok] = sq;
         }
     }
-    __syncwarp();
+    __syncthreads();
+    if (NORM) {
+        if (threadIdx.x < p.mc) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < WT; ++w) v += s_ss[w * (NT * 8) + threadIdx.x];
+            s_rstd[threadIdx.x] = rsqrtf(v / (float)p.K + p.eps);
+        }
+        __syncthreads();
+    }
+    stamp();
 
-    int it = 0;
+    int c_slot = 0;
+    uint32_t c_parity = 0;
     for (int ti = 0; ti < my_tiles; ++ti) {
-        const int st = (int)blockIdx.x + ti * (int)gridDim.x;
+        const int st = tile0 + ti * tile_stride;
         float acc[2][NT][4];
 #pragma unroll
         for (int a = 0; a < 2; ++a)
@@ -156,9 +212,14 @@ __global__ void __launch_bounds__(WARPS * 32, ((NT <= 2 && WARPS == 8) ? 2 : 1))
 #pragma unroll
                 for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
 
-        for (int i = 0; i < ng; ++i, ++it) {
-            const int s = it % STAGES;
-            const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
+        for (int i = 0; i < ng; ++i) {
+            const int s = c_slot;
+            const uint32_t parity = c_parity;
+            if (++c_slot == STAGES) {
+                c_slot = 0;
+                c_parity ^= 1u;
+            }
+            const int gi = g_begin + i;
             // B fragments: 32 contiguous bytes of each piece per lane
             uint4 bh[NT][2], bl[NT][2];
             int2 tab[NT][2];
@@ -166,8 +227,8 @@ __global__ void __launch_bounds__(WARPS * 32, ((NT <= 2 && WARPS == 8) ? 2 : 1))
             for (int nt = 0; nt < NT; ++nt) {
                 const int tok = nt * 8 + g;
                 if (tok < p.mc) {
-                    const uint8_t* ph = xw_hi + tok * row_b + i * 128 + t * 32;
-                    const uint8_t* pl = xw_lo + tok * row_b + i * 128 + t * 32;
+                    const uint8_t* ph = xs_hi + tok * row_b + gi * 128 + t * 32;
+                    const uint8_t* pl = xs_lo + tok * row_b + gi * 128 + t * 32;
                     bh[nt][0] = *reinterpret_cast<const uint4*>(ph);
                     bh[nt][1] = *reinterpret_cast<const uint4*>(ph + 16);
                     bl[nt][0] = *reinterpret_cast<const uint4*>(pl);
@@ -179,7 +240,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((NT <= 2 && WARPS == 8) ? 2 : 1))
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int tc = nt * 8 + 2 * t + e;
-                    tab[nt][e] = tc < p.mc ? xw_tab[i * p.mc + tc] : make_int2(0, 0);
+                    tab[nt][e] = tc < p.mc ? xs_tab[gi * p.mc + tc] : make_int2(0, 0);
                 }
             }
 
@@ -240,14 +301,20 @@ __global__ void __launch_bounds__(WARPS * 32, ((NT <= 2 && WARPS == 8) ? 2 : 1))
                 }
             }
             __syncwarp();
-            if (lane == 0 && it + STAGES < total) {
-                mbar_expect_tx(&bars[s], kW4BlockBytes);
-                bulk_g2s(ring + s * kW4BlockBytes, item_src(it + STAGES), kW4BlockBytes, &bars[s]);
+            if (lane == 0) {
+                if (p_issued < total) {
+                    issue_next();   // refills the slot just drained (p_slot == s)
+                } else if (p_issued == total && p.pf_ptr) {
+                    // this warp has requested its last block: HBM starts to idle -> pull the next kernel's weights into L2
+                    l2_prefetch_share(p.pf_ptr, (size_t)p.pf_bytes, (int)blockIdx.x * WT + warp, (int)gridDim.x * WT);
+                    ++p_issued;   // once
+                }
             }
         }
 
-        // ---- split-k reduction across the warps + epilogue (same as v2) ----
-        float* myred = red + (S::kRedBufs == 2 ? (ti & 1) * S::kRedFloats : 0) + warp * (NT * 8 * 32);
+        // ---- split-k reduction across the warps of this sub-CTA + epilogue ----
+        float* rbuf = red + (S::kRedBufs == 2 ? (ti & 1) * S::kRedFloats : 0);
+        float* myred = rbuf + wl * (NT * 8 * 32);
 #pragma unroll
         for (int tt = 0; tt < 2; ++tt)
 #pragma unroll
@@ -259,28 +326,19 @@ __global__ void __launch_bounds__(WARPS * 32, ((NT <= 2 && WARPS == 8) ? 2 : 1))
                 myred[tok * 32 + row + 8] = acc[tt][nt][2];
                 myred[(tok + 1) * 32 + row + 8] = acc[tt][nt][3];
             }
-        __syncthreads();
-        if (NORM && ti == 0) {
-            if (threadIdx.x < p.mc) {
-                float v = 0.f;
-#pragma unroll
-                for (int w = 0; w < WARPS; ++w) v += s_ss[w * (NT * 8) + threadIdx.x];
-                s_rstd[threadIdx.x] = rsqrtf(v / (float)p.K + p.eps);
-            }
-            __syncthreads();
-        }
+        sub_barrier(1 + sub, WARPS * 32);
 
-        const float* rbase = red + (S::kRedBufs == 2 ? (ti & 1) * S::kRedFloats : 0);
         auto sum_red = [&](int idx) {
             float v = 0.f;
 #pragma unroll
-            for (int w = 0; w < WARPS; ++w) v += rbase[w * (NT * 8 * 32) + idx];
+            for (int w = 0; w < WARPS; ++w) v += rbuf[w * (NT * 8 * 32) + idx];
             return v;
         };
         const int n0 = st * 32;
+        constexpr int kSubThreads = WARPS * 32;
         if (p.epi == ZL_EPI_SWIGLU) {
             const int n_out = p.N / 2;
-            for (int e = threadIdx.x; e < p.mc * 16; e += blockDim.x) {
+            for (int e = stid; e < p.mc * 16; e += kSubThreads) {
                 const int tok = e >> 4, oc = e & 15;
                 const int rg = (oc >> 3) * 16 + (oc & 7);
                 float gate = sum_red(tok * 32 + rg);
@@ -301,7 +359,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((NT <= 2 && WARPS == 8) ? 2 : 1))
             const int d = p.dim_head, half_dim = d / 2;
             const int tiles_per_head = d / 32;
             const int head = st / tiles_per_head, jt = st % tiles_per_head;
-            for (int e = threadIdx.x; e < p.mc * 16; e += blockDim.x) {
+            for (int e = stid; e < p.mc * 16; e += kSubThreads) {
                 const int tok = e >> 4, oc = e & 15;
                 const int rlo = (oc >> 3) * 16 + (oc & 7);
                 const int c = jt * 16 + oc;
@@ -344,7 +402,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((NT <= 2 && WARPS == 8) ? 2 : 1))
                 }
             }
         } else {
-            for (int e = threadIdx.x; e < p.mc * 32; e += blockDim.x) {
+            for (int e = stid; e < p.mc * 32; e += kSubThreads) {
                 const int tok = e >> 5, row = e & 31;
                 float v = sum_red(tok * 32 + row);
                 if (NORM) v *= s_rstd[tok];
@@ -355,7 +413,8 @@ __global__ void __launch_bounds__(WARPS * 32, ((NT <= 2 && WARPS == 8) ? 2 : 1))
                 p.y[(size_t)tok * p.N + n0 + row] = h;
             }
         }
-        if (S::kRedBufs == 1) __syncthreads();
+        if (S::kRedBufs == 1) sub_barrier(1 + sub, WARPS * 32);
+        stamp();
     }
 }
 
@@ -370,71 +429,72 @@ static int v3_num_sms() {
     return n_sm;
 }
 
-constexpr int kV3TwoCtaBudget = 115000;
-constexpr int kV3OneCtaBudget = 231000;
+constexpr int kV3Budget = 231000;   // one CTA per SM (227 KB usable + 1 KB reserved)
 
-template <int NT, bool NORM, int WARPS, int STAGES>
+template <int NT, bool NORM, int WARPS, int SUBS, int STAGES>
 static cudaError_t launch_v3_t(const W4Params& p, int smem, bool pdl, cudaStream_t stream) {
     const int tiles = p.N / 32;
-    const int max_ctas = v3_num_sms() * (WARPS == 8 ? 2 : 1);
-    const int grid = tiles < max_ctas ? tiles : max_ctas;
-    return launch(k_w4a16_v3<NT, NORM, WARPS, STAGES>, dim3(grid), dim3(WARPS * 32), (size_t)smem, stream, pdl, p);
+    const int want = (tiles + SUBS - 1) / SUBS;
+    const int grid = want < v3_num_sms() ? want : v3_num_sms();
+    return launch(k_w4a16_v3<NT, NORM, WARPS, SUBS, STAGES>, dim3(grid), dim3(WARPS * SUBS * 32), (size_t)smem, stream,
+                  pdl, p);
 }
 
-template <int NT, int WARPS, int STAGES>
+template <int NT, int WARPS, int SUBS, int STAGES>
 static bool v3_try(const W4Params& p, bool pdl, cudaStream_t stream, cudaError_t* err) {
     const int G = p.K / kW4GroupK;
-    const int ng_max = (G + WARPS - 1) / WARPS;
-    const int smem = V3Smem<NT, WARPS, STAGES>::kBytes + WARPS * v3_warp_bytes(p.mc, ng_max);
-    if (smem > (WARPS == 8 ? kV3TwoCtaBudget : kV3OneCtaBudget)) return false;
-    *err = p.ln_w ? launch_v3_t<NT, true, WARPS, STAGES>(p, smem, pdl, stream)
-                  : launch_v3_t<NT, false, WARPS, STAGES>(p, smem, pdl, stream);
+    const int smem = V3Smem<NT, WARPS, SUBS, STAGES>::kBytes + v3_stage_bytes(p.mc, p.K);
+    if (G > 8 * WARPS * SUBS || smem > kV3Budget) return false;   // 8 = kMaxNg
+    *err = p.ln_w ? launch_v3_t<NT, true, WARPS, SUBS, STAGES>(p, smem, pdl, stream)
+                  : launch_v3_t<NT, false, WARPS, SUBS, STAGES>(p, smem, pdl, stream);
     return true;
+}
+
+static bool v3_is_tall(const W4Params& p) {
+    static int force = -1;
+    if (force < 0) {
+        const char* e = getenv("ZL_W4_TALL");
+        force = e ? atoi(e) : 0;
+    }
+    if (force == 1) return p.K / kW4GroupK >= 32;
+    if (force == 2) return false;
+    return p.N / 32 <= v3_num_sms() && p.K / kW4GroupK >= 32;
 }
 
 // returns false when the staged activations do not fit shared memory (caller falls back to the fp16 kernels)
 bool launch_w4_v3(const W4Params& p, bool pdl, cudaStream_t stream, cudaError_t* err) {
-    const bool tall = p.N / 32 <= v3_num_sms() && p.K / kW4GroupK >= 32;
+    const bool tall = v3_is_tall(p);
     if (p.mc <= 8) {
-        if (tall && v3_try<1, 16, 4>(p, pdl, stream, err)) return true;
-        if (v3_try<1, 8, 5>(p, pdl, stream, err)) return true;
-        if (v3_try<1, 8, 4>(p, pdl, stream, err)) return true;
-        return v3_try<1, 8, 3>(p, pdl, stream, err);
+        if (tall && v3_try<1, 16, 1, 4>(p, pdl, stream, err)) return true;
+        if (v3_try<1, 8, 2, 5>(p, pdl, stream, err)) return true;
+        return v3_try<1, 8, 2, 4>(p, pdl, stream, err);
     }
     if (p.mc <= 16) {
-        if (tall && v3_try<2, 16, 4>(p, pdl, stream, err)) return true;
-        return v3_try<2, 8, 4>(p, pdl, stream, err);
+        if (tall && v3_try<2, 16, 1, 4>(p, pdl, stream, err)) return true;
+        return v3_try<2, 8, 2, 4>(p, pdl, stream, err);
     }
     return false;
 }
 
 bool w4_v3_fits(int mc, int N, int K) {
     const int G = K / kW4GroupK;
-    auto fits = [&](int fixed, int warps, int budget) {
-        const int ng_max = (G + warps - 1) / warps;
-        return fixed + warps * v3_warp_bytes(mc, ng_max) <= budget;
-    };
-    const bool tall = N / 32 <= v3_num_sms() && G >= 32;
-    if (mc <= 8) {
-        if (tall && fits(V3Smem<1, 16, 4>::kBytes, 16, kV3OneCtaBudget)) return true;
-        return fits(V3Smem<1, 8, 3>::kBytes, 8, kV3TwoCtaBudget);
-    }
-    if (mc <= 16) {
-        if (tall && fits(V3Smem<2, 16, 4>::kBytes, 16, kV3OneCtaBudget)) return true;
-        return fits(V3Smem<2, 8, 4>::kBytes, 8, kV3TwoCtaBudget);
-    }
+    if (G > 8 * 16) return false;
+    const int stage = v3_stage_bytes(mc, K);
+    if (mc <= 8) return V3Smem<1, 8, 2, 4>::kBytes + stage <= kV3Budget;
+    if (mc <= 16) return V3Smem<2, 8, 2, 4>::kBytes + stage <= kV3Budget;
+    (void)N;
     return false;
 }
 
 cudaError_t prepare_w4_v3() {
     cudaError_t e;
-#define ZL_SET(NT, NORM, W, ST)                                                                              \
-    e = cudaFuncSetAttribute(k_w4a16_v3<NT, NORM, W, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                             W == 8 ? kV3TwoCtaBudget : kV3OneCtaBudget);                                     \
+#define ZL_SET(NT, NORM, W, SB, ST)                                                                            \
+    e = cudaFuncSetAttribute(k_w4a16_v3<NT, NORM, W, SB, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                             kV3Budget);                                                                        \
     if (e != cudaSuccess) return e;
-    ZL_SET(1, false, 8, 5) ZL_SET(1, true, 8, 5) ZL_SET(1, false, 16, 4) ZL_SET(1, true, 16, 4)
-    ZL_SET(1, false, 8, 4) ZL_SET(1, true, 8, 4) ZL_SET(1, false, 8, 3) ZL_SET(1, true, 8, 3)
-    ZL_SET(2, false, 8, 4) ZL_SET(2, true, 8, 4) ZL_SET(2, false, 16, 4) ZL_SET(2, true, 16, 4)
+    ZL_SET(1, false, 8, 2, 5) ZL_SET(1, true, 8, 2, 5) ZL_SET(1, false, 8, 2, 4) ZL_SET(1, true, 8, 2, 4)
+    ZL_SET(1, false, 16, 1, 4) ZL_SET(1, true, 16, 1, 4)
+    ZL_SET(2, false, 8, 2, 4) ZL_SET(2, true, 8, 2, 4) ZL_SET(2, false, 16, 1, 4) ZL_SET(2, true, 16, 1, 4)
 #undef ZL_SET
     return cudaSuccess;
 }
