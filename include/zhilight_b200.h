@@ -206,10 +206,47 @@ int zl_embedding(const int32_t* ids, const void* table, void* out, int T, int D,
 size_t zl_argmax_workspace_bytes(int T);
 int zl_argmax(const float* logits, int32_t* out, int T, int V, void* workspace, size_t workspace_bytes, int pdl,
               zl_stream_t stream);
+/* vocab-parallel pick: per-token {float value, int global index} candidate of one logits shard (T, V), and the
+ * merge over the all-gathered candidates [ranks][stride] (embedding.cu:353-392 gathers the logits instead). */
+int zl_argmax_candidates(const float* logits, void* cand_out, int T, int V, int idx_offset, void* workspace,
+                         size_t workspace_bytes, int pdl, zl_stream_t stream);
+int zl_argmax_merge(const void* cand_all, int32_t* out, int T, int ranks, int stride, int pdl, zl_stream_t stream);
 /* synthetic-checkpoint generators (bench / tests): counter-based hash RNG, reproducible per seed. */
 int zl_fill_random_u32(uint32_t* p, size_t n, uint64_t seed, zl_stream_t stream);
 int zl_fill_const_u32(uint32_t* p, size_t n, uint32_t value, zl_stream_t stream);
 int zl_fill_uniform(void* p, size_t n, float lo, float hi, uint64_t seed, int dtype, zl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Tensor-parallel exchange over NVLink peer memory (one process per GPU, one node)
+ * Replaces ModelContext::reduce_sum / reduce_sum2 / reduce_tp_int8 (src/model/model_context.cpp:203-326) and
+ * the c10d NCCL wrappers it calls (3rd/bmengine/bmengine/c10d/c10d.cpp:42-136) on the decode path.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct zl_comm zl_comm_t;
+/* Allocates this rank's symmetric buffer (inboxes for world_size sources x 2 parities of max_elems 16-bit values). */
+int zl_comm_create(int rank, int world_size, size_t max_elems_16bit, zl_comm_t** out);
+void zl_comm_destroy(zl_comm_t* c);
+int zl_comm_rank(zl_comm_t* c);
+int zl_comm_world_size(zl_comm_t* c);
+/* CUDA IPC handle of the symmetric buffer (zl_comm_ipc_handle_bytes() bytes); exchange them out of band
+ * (torch.distributed all_gather in zhilight_b200/dist.py) and hand all of them (index = rank) to open_peers. */
+int zl_comm_ipc_handle_bytes(void);
+int zl_comm_get_ipc_handle(zl_comm_t* c, void* handle_out);
+int zl_comm_open_peers(zl_comm_t* c, const void* handles_all);
+/* out = T(T(sum over ranks of partial) + residual); n % 32 == 0; residual may be NULL; out may alias residual.
+ * int8_payload != 0: peers' contributions travel as int8 + one T scale per 32 values (the reference's group-32
+ * format, int8/quant_reduce_kernel.cu:14-38); deterministic rank-ordered fp32 reduction either way. */
+int zl_allreduce_one_shot(zl_comm_t* c, const void* partial, const void* residual, void* out, size_t n, int dtype,
+                          int int8_payload, int pdl, zl_stream_t stream);
+/* out[r*bytes ..] = `in` of rank r (bytes % 16 == 0, small: one CTA). */
+int zl_allgather_small(zl_comm_t* c, const void* in, void* out, size_t bytes, int pdl, zl_stream_t stream);
+/* int8_op::quant_group_32 / dequant_sum_quant_g32 / dequant_group_32 / dequant_group_fuse_add
+ * (src/nn/quant/int8/quant_reduce_kernel.cu:14-38, 243-322, 105-140, 201-240); M = number of 32-groups. */
+int zl_quant_group_32(const void* in, int8_t* out_q, void* out_scale, size_t M, int dtype, zl_stream_t stream);
+int zl_dequant_sum_quant_g32(const void* my, const int8_t* q_others, const void* scale_others, int8_t* out_q,
+                             void* out_scale, size_t M, int world_size, int dtype, zl_stream_t stream);
+/* add != NULL: dequant_group_fuse_add (out = q*s + add). */
+int zl_dequant_group_32(const int8_t* q, const void* scale, const void* add, void* out, size_t M, int dtype,
+                        zl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------ *
  * Decode driver: the model::LLaMA::encode + get_logits + greedy pick stand-in
@@ -230,10 +267,13 @@ typedef struct zl_llama_config {
     int max_batch, max_seq;
     int tp_rank, tp_size;
     int use_pdl, use_graph;
+    int tp_int8; /* TP all-reduce payload: 0 = activation dtype, 1 = int8 group-32 (REDUCE_TP_INT8 of the reference) */
     int fuse; /* 0: one kernel per reference operator; 1: RMSNorm folded into the W4 GEMMs; 2: + qkv RoPE/KV-append epilogue */
 } zl_llama_config_t;
 
 int zl_llama_create(const zl_llama_config_t* cfg, zl_llama_t** out);
+/* tensor parallel: hand the driver its exchange object (zl_comm_create + open_peers) before the first step. */
+int zl_llama_set_comm(zl_llama_t* m, zl_comm_t* comm);
 void zl_llama_destroy(zl_llama_t* m);
 /* Stage one checkpoint tensor (HOST pointer, row-major (rows, cols)); names as produced by
  * zhilight/loader.py:250-358 without the "llama." prefix, e.g. "layers.0.attn.project_q.qweight". */

@@ -309,3 +309,13 @@ def allreduce_exact(partials, dtype="f16"):
     for p in partials:
         s = s + np.asarray(p, dtype=F32)
     return _t(s, dtype)
+
+
+def allreduce_int8_one_shot(partials, dtype="f16"):
+    """The one-shot variant our NVLink kernel implements (zhilight_b200/csrc/comm.cu): every rank's contribution is
+    quantised ONCE with quant_group_32 and all ranks add the same ws dequantised vectors in rank order in fp32."""
+    acc = np.zeros(partials[0].size, dtype=F32).reshape(-1, 32)
+    for p in partials:
+        q, s = quant_group_32(np.asarray(p, dtype=F32).reshape(-1, 32), dtype)
+        acc = acc + q.astype(F32) * np.asarray(s, dtype=F32)[:, None]
+    return _t(acc, dtype).reshape(partials[0].shape)

@@ -68,6 +68,10 @@ struct zl_llama {
     size_t attn_ws_bytes = 0;
     void* argmax_ws = nullptr;
     int32_t* h_stage = nullptr;   // pinned: tokens | pos | lens | next
+    zl_comm_t* comm = nullptr;            // TP exchange (set by zl_llama_set_comm when tp_size > 1)
+    int vshard = 0;                       // vocabulary rows of lm_head held by this rank
+    void* cand = nullptr;                 // [B] {float value, int index} local argmax candidates
+    void* cand_all = nullptr;             // [tp][B] gathered candidates
     std::map<long long, cudaGraphExec_t> graphs;   // key = B * 2^32 + attention length bucket
     int cur_max_len = 0;                            // host-side upper bound of buf_lens (positions + 1)
     double weight_bytes = 0;
@@ -338,8 +342,9 @@ int finalize_globals(zl_llama* m) {
     m->weight_bytes -= (double)c.vocab_size * c.dim_model * 2;   // the embedding table is gathered, not streamed
     RCHECK(take_vector(m, "output_layernorm.weight", c.dim_model, &m->ln_f));
     if (find(m, "lm_head.weight")) {
-        RCHECK(take_vector(m, "lm_head.weight", c.vocab_size * c.dim_model, &m->lm_head));
+        RCHECK(take_vector(m, "lm_head.weight", m->vshard * c.dim_model, &m->lm_head));   // vocab-parallel shard
     } else {
+        ZL_CHECK_SUPPORTED(c.tp_size == 1);   // tied lm_head is only wired for a single rank
         m->lm_head = m->emb;   // tied (Llama-3.2-1B)
         m->lm_head_tied = true;
         m->weight_bytes += (double)c.vocab_size * c.dim_model * 2;
@@ -369,6 +374,8 @@ int alloc_runtime(zl_llama* m) {
     RCHECK(dmalloc(&m->gu, (size_t)B * 2 * m->ff * 2));
     RCHECK(dmalloc(&m->act, (size_t)B * m->ff * 2));
     RCHECK(dmalloc((void**)&m->logits, (size_t)B * c.vocab_size * 4));
+    RCHECK(dmalloc(&m->cand, (size_t)((B * 8 + 15) / 16) * 16));
+    RCHECK(dmalloc(&m->cand_all, (size_t)((B * 8 + 15) / 16) * 16 * c.tp_size));
     RCHECK(dmalloc((void**)&m->cosb, (size_t)B * d * 4));
     RCHECK(dmalloc((void**)&m->sinb, (size_t)B * d * 4));
     RCHECK(dmalloc((void**)&m->d_tokens, B * 4));
@@ -461,6 +468,11 @@ int enqueue_step(zl_llama* m, int B, int len_bucket) {
     const int D = c.dim_model, d = c.dim_head, dt = c.dtype, pdl = c.use_pdl;
     cudaStream_t st = m->stream;
     const bool w4 = c.quant_type == 5 || c.quant_type == 6;
+    const bool tp = c.tp_size > 1;
+    if (tp && !m->comm) {
+        zl_set_last_error(__FILE__, __LINE__, "tp_size > 1 but zl_llama_set_comm was not called");
+        return ZL_ERR_STATE;
+    }
     const float scale = 1.0f / sqrtf((float)d);   // attention.cpp:89
 
     ZL_CHECK_CUDA(launch(k_lens_from_pos, dim3(cdiv(B, 64)), dim3(64), 0, st, false, (const int32_t*)m->d_pos,
@@ -499,8 +511,14 @@ int enqueue_step(zl_llama* m, int B, int len_bucket) {
             RCHECK(zl_decode_attention(m->q, m->d_lens, L.k_addrs, L.v_addrs, nullptr, scale, len_bucket, m->ao, B, 1,
                                        m->hq, m->hkv, d, 1, m->attn_ws, m->attn_ws_bytes, dt, pdl, st));
         if (w4) {
-            if (!(skip & 4))
+            if (skip & 4) {
+            } else if (tp) {
+                // row-parallel: partial sums -> one-shot NVLink all-reduce fused with the residual add
+                RCHECK(w4_gemm(m, m->ao, m->hq * d, L.q_o, nullptr, m->pend, B, ZL_EPI_NONE, nullptr, nullptr, &L.q_gu));
+                RCHECK(zl_allreduce_one_shot(m->comm, m->pend, m->h, m->h, (size_t)B * D, dt, c.tp_int8, pdl, st));
+            } else {
                 RCHECK(w4_gemm(m, m->ao, m->hq * d, L.q_o, m->h, m->h, B, ZL_EPI_RESIDUAL, nullptr, nullptr, &L.q_gu));
+            }
             const void* xin = m->xn;
             const void* lnw = nullptr;
             if (c.fuse >= 1) {
@@ -510,18 +528,25 @@ int enqueue_step(zl_llama* m, int B, int len_bucket) {
                 RCHECK(zl_rmsnorm(m->h, L.ln_ff, m->xn, B, D, c.eps, 1.f, dt, pdl, st));
             }
             if (!(skip & 8)) RCHECK(w4_gemm(m, xin, D, L.q_gu, nullptr, m->act, B, ZL_EPI_SWIGLU, lnw, nullptr, &L.q_down));
-            if (!(skip & 16))
-                RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, m->h, m->h, B, ZL_EPI_RESIDUAL, nullptr, nullptr,
-                               l + 1 < c.num_layers ? &m->layers[l + 1].q_qkv : nullptr));
+            const W4Lin* nxt = l + 1 < c.num_layers ? &m->layers[l + 1].q_qkv : nullptr;
+            if (skip & 16) {
+            } else if (tp) {
+                RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, nullptr, m->pend, B, ZL_EPI_NONE, nullptr, nullptr, nxt));
+                RCHECK(zl_allreduce_one_shot(m->comm, m->pend, m->h, m->h, (size_t)B * D, dt, c.tp_int8, pdl, st));
+            } else {
+                RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, m->h, m->h, B, ZL_EPI_RESIDUAL, nullptr, nullptr, nxt));
+            }
         } else {
             RCHECK(zl_dense_gemm_skinny(m->ao, m->hq * d, L.d_o.w, L.d_o.bias, m->pend, B, D, m->hq * d, dt, dt, pdl,
                                         st));
+            if (tp) RCHECK(zl_allreduce_one_shot(m->comm, m->pend, nullptr, m->pend, (size_t)B * D, dt, c.tp_int8, pdl, st));
             RCHECK(zl_add_rmsnorm(m->h, m->pend, L.ln_ff, m->h, m->xn, B, D, c.eps, 1.f, 0, dt, pdl, st));
             RCHECK(zl_dense_gemm_skinny(m->xn, D, L.d_gu.w, L.d_gu.bias, m->gu, B, 2 * m->ff, D, dt, dt, pdl, st));
             RCHECK(zl_gate_mul(m->gu, 2 * m->ff, (char*)m->gu + (size_t)m->ff * 2, 2 * m->ff, m->act, m->ff, B,
                                m->ff, 0, dt, st));
             RCHECK(zl_dense_gemm_skinny(m->act, m->ff, L.d_down.w, L.d_down.bias, m->pend, B, D, m->ff, dt, dt, pdl,
                                         st));
+            if (tp) RCHECK(zl_allreduce_one_shot(m->comm, m->pend, nullptr, m->pend, (size_t)B * D, dt, c.tp_int8, pdl, st));
         }
     }
     if (w4) {
@@ -529,9 +554,19 @@ int enqueue_step(zl_llama* m, int B, int len_bucket) {
     } else {
         RCHECK(zl_add_rmsnorm(m->h, m->pend, m->ln_f, m->h, m->xn, B, D, c.eps, 1.f, 0, dt, pdl, st));
     }
+    // vocab-parallel lm_head (embedding.cu:353-392): each rank owns vshard rows
     if (!(skip & 32))
-        RCHECK(zl_dense_gemm_skinny(m->xn, D, m->lm_head, nullptr, m->logits, B, c.vocab_size, D, dt, ZL_F32, pdl, st));
-    RCHECK(zl_argmax(m->logits, m->d_next, B, c.vocab_size, m->argmax_ws, zl_argmax_workspace_bytes(B), pdl, st));
+        RCHECK(zl_dense_gemm_skinny(m->xn, D, m->lm_head, nullptr, m->logits, B, m->vshard, D, dt, ZL_F32, pdl, st));
+    if (!tp) {
+        RCHECK(zl_argmax(m->logits, m->d_next, B, m->vshard, m->argmax_ws, zl_argmax_workspace_bytes(B), pdl, st));
+    } else {
+        // instead of all-gathering (B, V) logits, exchange one {value, index} candidate per token
+        const int stride = ((B * 8 + 15) / 16) * 2;   // int2 records per rank slot (16-byte multiple)
+        RCHECK(zl_argmax_candidates(m->logits, m->cand, B, m->vshard, c.tp_rank * m->vshard, m->argmax_ws,
+                                    zl_argmax_workspace_bytes(B), pdl, st));
+        RCHECK(zl_allgather_small(m->comm, m->cand, m->cand_all, (size_t)stride * 8, pdl, st));
+        RCHECK(zl_argmax_merge(m->cand_all, m->d_next, B, c.tp_size, stride, pdl, st));
+    }
     return ZL_OK;
 }
 
@@ -580,7 +615,8 @@ extern "C" int zl_llama_create(const zl_llama_config_t* cfg, zl_llama_t** out) {
     ZL_CHECK_SUPPORTED(cfg->quant_type == 0 || cfg->dtype == ZL_F16);   // "A must be half" q_gemm_k_major.cu:989
     ZL_CHECK_SUPPORTED(cfg->dtype == ZL_F16 || cfg->dtype == ZL_BF16);
     ZL_CHECK_SUPPORTED(cfg->tp_size >= 1 && cfg->tp_rank >= 0 && cfg->tp_rank < cfg->tp_size);
-    ZL_CHECK_SUPPORTED(cfg->tp_size == 1);   // TP goes through zl_comm; not wired in the driver yet
+    ZL_CHECK_SUPPORTED(cfg->num_heads % cfg->tp_size == 0 && cfg->num_kv_heads % cfg->tp_size == 0 &&
+                       cfg->dim_ff % cfg->tp_size == 0 && cfg->vocab_size % cfg->tp_size == 0);
     ZL_CHECK_SUPPORTED(cfg->quant_type == 0 || cfg->group_size == zl::kW4GroupK);
     ZL_CHECK_ARG(cfg->fuse >= 0 && cfg->fuse <= 2);
     ZL_CHECK_SUPPORTED(cfg->fuse < 2 || cfg->dim_head % 32 == 0);
@@ -590,6 +626,7 @@ extern "C" int zl_llama_create(const zl_llama_config_t* cfg, zl_llama_t** out) {
     m->hq = cfg->num_heads / cfg->tp_size;
     m->hkv = cfg->num_kv_heads / cfg->tp_size;
     m->ff = cfg->dim_ff / cfg->tp_size;
+    m->vshard = cfg->vocab_size / cfg->tp_size;
     m->layers.resize(cfg->num_layers);
     if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete m;
@@ -597,6 +634,13 @@ extern "C" int zl_llama_create(const zl_llama_config_t* cfg, zl_llama_t** out) {
         return ZL_ERR_CUDA;
     }
     *out = m;
+    return ZL_OK;
+}
+
+extern "C" int zl_llama_set_comm(zl_llama_t* m, zl_comm_t* comm) {
+    ZL_CHECK_ARG(m && comm);
+    ZL_CHECK_ARG(zl_comm_world_size(comm) == m->cfg.tp_size && zl_comm_rank(comm) == m->cfg.tp_rank);
+    m->comm = comm;
     return ZL_OK;
 }
 
@@ -714,7 +758,7 @@ extern "C" int zl_llama_init_synthetic(zl_llama_t* m, uint64_t seed) {
     }
     RCHECK(stage_random(m, "token_embedding.weight", c.vocab_size, D, 2, 2, -0.035f, 0.035f, seed));
     RCHECK(stage_random(m, "output_layernorm.weight", 1, D, 2, 2, 0.9f, 1.1f, seed));
-    RCHECK(stage_random(m, "lm_head.weight", c.vocab_size, D, 2, 2, -0.035f, 0.035f, seed));
+    RCHECK(stage_random(m, "lm_head.weight", m->vshard, D, 2, 2, -0.035f, 0.035f, seed + 7919 * c.tp_rank));
     return zl_llama_finalize(m);
 }
 
@@ -757,9 +801,9 @@ extern "C" int zl_llama_decode(zl_llama_t* m, const int32_t* tokens_host, const 
     RCHECK(zl_llama_set_state(m, tokens_host, positions_host, B));
     RCHECK(run_step(m, B));
     ZL_CHECK_CUDA(cudaMemcpyAsync(m->h_stage + 3 * B, m->d_next, B * 4, cudaMemcpyDeviceToHost, m->stream));
-    if (logits_host)
-        ZL_CHECK_CUDA(cudaMemcpyAsync(logits_host, m->logits, (size_t)B * m->cfg.vocab_size * 4,
-                                      cudaMemcpyDeviceToHost, m->stream));
+    if (logits_host)   // (B, vocab/tp) of this rank's shard
+        ZL_CHECK_CUDA(cudaMemcpyAsync(logits_host, m->logits, (size_t)B * m->vshard * 4, cudaMemcpyDeviceToHost,
+                                      m->stream));
     ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
     for (int i = 0; i < B; ++i) next_tokens_host[i] = m->h_stage[3 * B + i];
     return ZL_OK;

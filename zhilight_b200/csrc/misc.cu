@@ -105,6 +105,52 @@ __global__ void k_argmax_final(const float* __restrict__ pval, const int* __rest
     if (threadIdx.x == 0) out[tok] = bi;
 }
 
+// vocab-parallel greedy pick: per-token (value, global index) candidate of this rank's logits shard ...
+__global__ void k_argmax_cand(const float* __restrict__ pval, const int* __restrict__ pidx, int chunks, int idx_offset,
+                              int2* __restrict__ cand) {
+    pdl_trigger();
+    pdl_wait();
+    const int tok = blockIdx.x;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < chunks; i += 32) {
+        const float v = pval[tok * chunks + i];
+        const int id = pidx[tok * chunks + i];
+        if (v > best || (v == best && id < bi)) {
+            best = v;
+            bi = id;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) {
+            best = ov;
+            bi = oi;
+        }
+    }
+    if (threadIdx.x == 0) cand[tok] = make_int2(__float_as_int(best), bi + idx_offset);
+}
+// ... and the merge over the gathered candidates [ranks][stride] (ties -> lowest index, like the single-rank pick)
+__global__ void k_argmax_merge(const int2* __restrict__ cand_all, int ranks, int stride, int T, int32_t* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
+    const int tok = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tok >= T) return;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int r = 0; r < ranks; ++r) {
+        const int2 c = cand_all[(size_t)r * stride + tok];
+        const float v = __int_as_float(c.x);
+        if (v > best || (v == best && c.y < bi)) {
+            best = v;
+            bi = c.y;
+        }
+    }
+    out[tok] = bi;
+}
+
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;
     x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -160,6 +206,28 @@ extern "C" int zl_argmax(const float* logits, int32_t* out, int T, int V, void* 
                          pidx));
     ZL_CHECK_CUDA(launch(k_argmax_final, dim3(T), dim3(32), 0, stream, pdl != 0, (const float*)pval,
                          (const int*)pidx, chunks, out));
+    return ZL_OK;
+}
+
+extern "C" int zl_argmax_candidates(const float* logits, void* cand_out, int T, int V, int idx_offset, void* workspace,
+                                    size_t workspace_bytes, int pdl, zl_stream_t stream) {
+    ZL_CHECK_ARG(logits && cand_out && T > 0 && V > 0 && workspace);
+    const int chunks = 64;
+    ZL_CHECK_ARG(workspace_bytes >= zl_argmax_workspace_bytes(T));
+    float* pval = static_cast<float*>(workspace);
+    int* pidx = reinterpret_cast<int*>(pval + (size_t)T * chunks);
+    ZL_CHECK_CUDA(launch(k_argmax_partial, dim3(chunks, T), dim3(256), 0, stream, pdl != 0, logits, V, chunks, pval,
+                         pidx));
+    ZL_CHECK_CUDA(launch(k_argmax_cand, dim3(T), dim3(32), 0, stream, pdl != 0, (const float*)pval, (const int*)pidx,
+                         chunks, idx_offset, (int2*)cand_out));
+    return ZL_OK;
+}
+
+extern "C" int zl_argmax_merge(const void* cand_all, int32_t* out, int T, int ranks, int stride, int pdl,
+                               zl_stream_t stream) {
+    ZL_CHECK_ARG(cand_all && out && T > 0 && ranks > 0 && stride >= T);
+    ZL_CHECK_CUDA(launch(k_argmax_merge, dim3(cdiv(T, 64)), dim3(64), 0, stream, pdl != 0, (const int2*)cand_all, ranks,
+                         stride, T, out));
     return ZL_OK;
 }
 

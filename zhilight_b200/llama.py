@@ -29,19 +29,24 @@ QUANT_NONE, QUANT_GPTQ, QUANT_AWQ = 0, 5, 6     # model_config.hpp:132-144
 class LlamaDecoder:
     def __init__(self, num_layers, dim_model, num_heads, num_kv_heads, dim_head, dim_ff, vocab_size, eps=1e-5,
                  rope_theta=10000.0, rope_llama3=None, quant_type=QUANT_NONE, group_size=128, sym=False,
-                 dtype="f16", max_batch=1, max_seq=512, use_pdl=True, use_graph=True, tp_rank=0, tp_size=1, fuse=2):
+                 dtype="f16", max_batch=1, max_seq=512, use_pdl=True, use_graph=True, tp_rank=0, tp_size=1, fuse=2, tp_int8=False):
         self.lib = _lib.load()
         l3 = rope_llama3 or {}
         self.cfg = _lib.LlamaConfig(
             num_layers, dim_model, num_heads, num_kv_heads, dim_head, dim_ff, vocab_size, eps, rope_theta,
             float(l3.get("factor", 0.0)), float(l3.get("low", 1.0)), float(l3.get("high", 4.0)),
             float(l3.get("orig", 8192.0)), quant_type, group_size, int(sym), {"f16": 0, "bf16": 1}[dtype],
-            max_batch, max_seq, tp_rank, tp_size, int(use_pdl), int(use_graph), int(fuse))
+            max_batch, max_seq, tp_rank, tp_size, int(use_pdl), int(use_graph), int(tp_int8), int(fuse))
         self.vocab_size = vocab_size
         self.max_batch = max_batch
         h = ctypes.c_void_p()
         _lib.check(self.lib.zl_llama_create(ctypes.byref(self.cfg), ctypes.byref(h)))
         self.h = h
+
+    def set_comm(self, comm):
+        """comm: zhilight_b200.dist.TPComm (kept alive by this object)."""
+        self._comm = comm
+        _lib.check(self.lib.zl_llama_set_comm(self.h, comm.handle))
 
     def close(self):
         if getattr(self, "h", None):
