@@ -19,8 +19,9 @@ architecture in HF-GPTQ layout, synthetic prompt token ids ("data": "synthetic")
 --impl reference times that CPU path as the whole arm (the reference has no CPU implementation of its own;
 SURVEY.md section 8d names this torch dequant path as the side-by-side baseline).
 
-N > 1: this round the driver is single-GPU (tensor-parallel wiring is the next row, DESIGN.md section 7);
---gpus N runs N independent replicas, one per rank, and says so in config.parallelism.
+N > 1: tensor parallel over the N GPUs of one node (the reference's row/column split), one process per GPU; the
+partial sums of the row-parallel Linears are exchanged with the one-shot NVLink peer-memory all-reduce
+(zhilight_b200/csrc/comm.cu), NCCL only bootstraps.  value = tokens/s of the whole TP group ("scaling": "strong").
 """
 import argparse
 import json
@@ -191,6 +192,7 @@ def main():
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tp-int8", action="store_true", help="int8 group-32 payload for the TP all-reduce")
     ap.add_argument("--fuse", type=int, default=2, help="0: one kernel per reference op; 1: +RMSNorm fused; 2: +qkv RoPE/KV epilogue")
     args = ap.parse_args()
 
@@ -219,13 +221,18 @@ def main():
     from zhilight_b200.llama import LlamaDecoder
     build.build()
 
+    from zhilight_b200 import dist as zdist
     dense = args.model == "llama-3.2-1b"
     W = max(args.warmup, 3)
     max_seq = args.prompt + 2 * W + 2 * args.steps + 16
     dec = LlamaDecoder(quant_type=0 if dense else 5, group_size=128, sym=True, dtype="bf16" if dense else "f16",
                        max_batch=args.batch, max_seq=max_seq, use_pdl=not args.no_pdl, use_graph=not args.no_graph, fuse=args.fuse,
-                       **cfg)
-    dec.init_synthetic(seed=1 + rank)
+                       tp_rank=rank, tp_size=world, tp_int8=args.tp_int8, **cfg)
+    comm = None
+    if world > 1:
+        comm = zdist.TPComm(args.batch * cfg["dim_model"], rank, world)
+        dec.set_comm(comm)
+    dec.init_synthetic(seed=1)
     B = args.batch
     rng = np.random.default_rng(0)
     stream = torch.cuda.ExternalStream(dec.stream())
@@ -299,7 +306,7 @@ def main():
                 "bytes_per_launch": g_bytes / g_launches, "us_per_launch": g_ms * 1e3 / iters / g_launches,
                 "traffic": traffic}
 
-    tokens = B * args.steps * world
+    tokens = B * args.steps          # one TP group decodes B sequences, whatever its size
     value = tokens / (ms_dev * 1e-3)
     e2e_value = tokens / (ms_e2e * 1e-3)
     ctx_mid = args.prompt + W + args.steps // 2
@@ -309,10 +316,10 @@ def main():
 
     out = {
         "metric": "decode tokens/s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
-        "warmup": W, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": W, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
         "vs_baseline": None, "dtype": "bf16" if dense else "f16 (W4A16: int4 weights, fp16 activations, fp32 accumulate)",
         "data": "synthetic",
-        "config": {"workload": workload, "parallelism": "single GPU" if world == 1 else "dp%d replicas" % world,
+        "config": {"workload": workload, "parallelism": "single GPU" if world == 1 else "tp%d (one-shot NVLink all-reduce, %s payload)" % (world, "int8-g32" if args.tp_int8 else "fp16"),
                    "l2": "weights per step (%.2f GB) exceed L2 (126 MB); no explicit flush" % (weight_bytes / 1e9),
                    "pdl": not args.no_pdl, "cuda_graph": not args.no_graph, "fuse": args.fuse},
         "clocks": clocks,

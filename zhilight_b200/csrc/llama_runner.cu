@@ -10,6 +10,7 @@
 #include "w4_layout.cuh"
 
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <string>
 #include <vector>
@@ -401,13 +402,44 @@ static size_t prefetch_cap() {
     static long v = -1;
     if (v < 0) {
         const char* e = getenv("ZL_L2_PREFETCH_MB");
-        v = e ? atol(e) : 24;
+        v = e ? atol(e) : 0;   // measured on B200: bulk L2 prefetch competes with the ring's TMA traffic; off by default
     }
     return (size_t)v << 20;
 }
+// which blob each kernel of a layer prefetches (ZL_L2_PREFETCH_PLAN, 5 digits for qkv,attn(unused),o,gate_up,down ->
+// 0 none, 1 o, 2 gate_up, 3 down, 4 next qkv); experiment knob, only read when ZL_L2_PREFETCH_MB > 0
+static int prefetch_plan(int slot) {
+    static int plan[5] = {-1, 0, 0, 0, 0};
+    if (plan[0] < 0) {
+        const char* e = getenv("ZL_L2_PREFETCH_PLAN");
+        const char* d = (e && strlen(e) == 5) ? e : "10234";
+        for (int i = 0; i < 5; ++i) plan[i] = d[i] - '0';
+    }
+    return plan[slot];
+}
+
+// resolve the plan entry of kernel `slot` (0 qkv, 1 attention, 2 o, 3 gate_up, 4 down) of layer l to a packed blob
+static void prefetch_target(zl_llama* m, int l, int slot, int B, const void** ptr, size_t* bytes) {
+    *ptr = nullptr;
+    *bytes = 0;
+    const auto& c = m->cfg;
+    if (!(c.quant_type == 5 || c.quant_type == 6) || prefetch_cap() == 0) return;
+    const int what = prefetch_plan(slot);
+    const W4Lin* t = nullptr;
+    Layer& L = m->layers[l];
+    if (what == 1) t = &L.q_o;
+    else if (what == 2) t = &L.q_gu;
+    else if (what == 3) t = &L.q_down;
+    else if (what == 4 && l + 1 < c.num_layers) t = &m->layers[l + 1].q_qkv;
+    if (!t) return;
+    const bool t_int = t->packed_i && !getenv("ZL_W4_FORCE_HALF") && zl_w4_int_kernel_fits(B, t->N, t->K);
+    *ptr = t_int ? t->packed_i : t->packed;
+    const size_t nb = zl_w4_packed_bytes(t->N, t->K, c.group_size);
+    *bytes = nb < prefetch_cap() ? nb : prefetch_cap();
+}
 
 int w4_gemm(zl_llama* m, const void* x, int ldx, const W4Lin& w, const void* residual, void* y, int B, int epi,
-            const void* ln_w, const Layer* rope_layer, const W4Lin* next = nullptr) {
+            const void* ln_w, const Layer* rope_layer, int layer = -1, int slot = -1) {
     const auto& c = m->cfg;
     zl_w4_fused_args_t a = {};
     a.x = x;
@@ -415,11 +447,10 @@ int w4_gemm(zl_llama* m, const void* x, int ldx, const W4Lin& w, const void* res
     const bool use_int = w.packed_i && !getenv("ZL_W4_FORCE_HALF") && zl_w4_int_kernel_fits(B, w.N, w.K);
     a.packed = use_int ? w.packed_i : w.packed;
     a.variant = use_int ? 1 : 0;
-    if (next && prefetch_cap() > 0) {
-        const bool next_int = next->packed_i && !getenv("ZL_W4_FORCE_HALF") && zl_w4_int_kernel_fits(B, next->N, next->K);
-        a.prefetch_ptr = next_int ? next->packed_i : next->packed;
-        const size_t nb = zl_w4_packed_bytes(next->N, next->K, c.group_size);
-        a.prefetch_bytes = nb < prefetch_cap() ? nb : prefetch_cap();
+    if (layer >= 0) {
+        size_t nb = 0;
+        prefetch_target(m, layer, slot, B, &a.prefetch_ptr, &nb);
+        a.prefetch_bytes = nb;
     }
     if (!a.packed) {
         zl_set_last_error(__FILE__, __LINE__, "no packed weight variant for this batch size");
@@ -493,9 +524,9 @@ int enqueue_step(zl_llama* m, int B, int len_bucket) {
             }
             if (skip & 2) {
             } else if (c.fuse >= 2) {
-                RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, nullptr, B, ZL_EPI_QKV_ROPE, lnw, &L, &L.q_o));
+                RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, nullptr, B, ZL_EPI_QKV_ROPE, lnw, &L, l, 0));
             } else {
-                RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, m->qkv, B, ZL_EPI_NONE, lnw, nullptr, &L.q_o));
+                RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, m->qkv, B, ZL_EPI_NONE, lnw, nullptr, l, 0));
             }
         } else {
             // residual of the previous layer's FFN is folded into this norm (block.cpp:139-141 + 131)
@@ -514,10 +545,10 @@ int enqueue_step(zl_llama* m, int B, int len_bucket) {
             if (skip & 4) {
             } else if (tp) {
                 // row-parallel: partial sums -> one-shot NVLink all-reduce fused with the residual add
-                RCHECK(w4_gemm(m, m->ao, m->hq * d, L.q_o, nullptr, m->pend, B, ZL_EPI_NONE, nullptr, nullptr, &L.q_gu));
+                RCHECK(w4_gemm(m, m->ao, m->hq * d, L.q_o, nullptr, m->pend, B, ZL_EPI_NONE, nullptr, nullptr, l, 2));
                 RCHECK(zl_allreduce_one_shot(m->comm, m->pend, m->h, m->h, (size_t)B * D, dt, c.tp_int8, pdl, st));
             } else {
-                RCHECK(w4_gemm(m, m->ao, m->hq * d, L.q_o, m->h, m->h, B, ZL_EPI_RESIDUAL, nullptr, nullptr, &L.q_gu));
+                RCHECK(w4_gemm(m, m->ao, m->hq * d, L.q_o, m->h, m->h, B, ZL_EPI_RESIDUAL, nullptr, nullptr, l, 2));
             }
             const void* xin = m->xn;
             const void* lnw = nullptr;
@@ -527,14 +558,13 @@ int enqueue_step(zl_llama* m, int B, int len_bucket) {
             } else {
                 RCHECK(zl_rmsnorm(m->h, L.ln_ff, m->xn, B, D, c.eps, 1.f, dt, pdl, st));
             }
-            if (!(skip & 8)) RCHECK(w4_gemm(m, xin, D, L.q_gu, nullptr, m->act, B, ZL_EPI_SWIGLU, lnw, nullptr, &L.q_down));
-            const W4Lin* nxt = l + 1 < c.num_layers ? &m->layers[l + 1].q_qkv : nullptr;
+            if (!(skip & 8)) RCHECK(w4_gemm(m, xin, D, L.q_gu, nullptr, m->act, B, ZL_EPI_SWIGLU, lnw, nullptr, l, 3));
             if (skip & 16) {
             } else if (tp) {
-                RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, nullptr, m->pend, B, ZL_EPI_NONE, nullptr, nullptr, nxt));
+                RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, nullptr, m->pend, B, ZL_EPI_NONE, nullptr, nullptr, l, 4));
                 RCHECK(zl_allreduce_one_shot(m->comm, m->pend, m->h, m->h, (size_t)B * D, dt, c.tp_int8, pdl, st));
             } else {
-                RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, m->h, m->h, B, ZL_EPI_RESIDUAL, nullptr, nullptr, nxt));
+                RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, m->h, m->h, B, ZL_EPI_RESIDUAL, nullptr, nullptr, l, 4));
             }
         } else {
             RCHECK(zl_dense_gemm_skinny(m->ao, m->hq * d, L.d_o.w, L.d_o.bias, m->pend, B, D, m->hq * d, dt, dt, pdl,

@@ -108,7 +108,17 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
         }
     };
 
-    unsigned long long* tr = p.trace ? p.trace + (size_t)blockIdx.x * 16 : nullptr;
+    // debug timeline: dbg & 2 -> one record per LAUNCH (CTA 0 claims a slot: trace[0] is the launch counter),
+    // otherwise one record per CTA
+    unsigned long long* tr = nullptr;
+    if (p.trace) {
+        if (p.dbg & 2) {
+            if (blockIdx.x == 0 && threadIdx.x == 0)
+                tr = p.trace + 8 + (size_t)atomicAdd(p.trace, 1ull) * 16;
+        } else {
+            tr = p.trace + (size_t)blockIdx.x * 16;
+        }
+    }
     int tr_n = 0;
     auto stamp = [&]() {
         if (tr && threadIdx.x == 0 && tr_n < 16) tr[tr_n++] = globaltimer_ns();
@@ -122,6 +132,9 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
 #pragma unroll
         for (int s = 0; s < STAGES; ++s)
             if (s < total) issue_next();
+        // software-managed L2: start pulling the weights of a LATER kernel of the chain into the 126 MB L2 now, so
+        // that HBM keeps streaming while this kernel and its neighbours sit in their latency-bound phases
+        if (p.pf_ptr) l2_prefetch_share(p.pf_ptr, (size_t)p.pf_bytes, (int)blockIdx.x * WT + warp, (int)gridDim.x * WT);
     }
     // staging assignment: group gi -> warp gi % WT.  RMSNorm weights are constants: fetch them before the wait.
     constexpr int kMaxNg = 8;   // groups per warp kept in registers during staging (K <= 8*WT*128)
@@ -301,15 +314,7 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
                 }
             }
             __syncwarp();
-            if (lane == 0) {
-                if (p_issued < total) {
-                    issue_next();   // refills the slot just drained (p_slot == s)
-                } else if (p_issued == total && p.pf_ptr) {
-                    // this warp has requested its last block: HBM starts to idle -> pull the next kernel's weights into L2
-                    l2_prefetch_share(p.pf_ptr, (size_t)p.pf_bytes, (int)blockIdx.x * WT + warp, (int)gridDim.x * WT);
-                    ++p_issued;   // once
-                }
-            }
+            if (lane == 0 && p_issued < total) issue_next();   // refills the slot just drained (p_slot == s)
         }
 
         // ---- split-k reduction across the warps of this sub-CTA + epilogue ----
