@@ -99,7 +99,8 @@ def cpu_reference_path(cfg, quant, batch, budget_s=20.0, threads=None):
     import numpy as np
     import torch
     from oracle import gptq
-    threads = threads or os.cpu_count()
+    # torch's bf16 matmul stops scaling (and oversubscribes badly) beyond a few dozen threads
+    threads = threads or min(os.cpu_count() or 1, 32)
     torch.set_num_threads(threads)
     d_model, d, ff, v = cfg["dim_model"], cfg["dim_head"], cfg["dim_ff"], cfg["vocab_size"]
     shapes = [(d_model, cfg["num_heads"] * d), (d_model, cfg["num_kv_heads"] * d), (d_model, cfg["num_kv_heads"] * d),
@@ -298,10 +299,10 @@ def main():
     tp = os.path.join(ROOT, "profiles", "r01_w4a16_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch") if (not dense and B == 1 and world == 1) else None
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_dense_skinny" if dense else "k_w4a16_mma<1>" if B <= 8 else "k_w4a16_mma",
+    roofline = {"bound": "hbm", "kernel": "k_dense_skinny" if dense else "k_w4a16_v3 (integer IMMA; k_w4a16_v2 where its staging does not fit)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
                 "bytes_per_launch": g_bytes / g_launches, "us_per_launch": g_ms * 1e3 / iters / g_launches,
                 "traffic": traffic}

@@ -134,6 +134,27 @@ int zl_qkv_rope_row_map(int32_t* row_map, int n_heads_total, int dim_head, zl_st
 /* dst[i] = src[map[i]] for 16-bit elements (bias permutation to packed-row order). */
 int zl_gather_rows_16(const void* src, const int32_t* map, void* dst, int n, zl_stream_t stream);
 
+/* ---- W8A8 Linear: SmoothQuant INT8 (Int8Linear, src/nn/linear/linear.cpp:432-636) and per-tensor FP8 e4m3
+ * (Fp8Linear, linear.cpp:1612-1695) ---------------------------------------------------------------------- */
+enum { ZL_W8_INT8 = 0, ZL_W8_FP8 = 1 };
+/* int8_op::quant_calc_scale (src/nn/quant/int8/quant_kernel.cu:15-103): per-token absmax quantisation,
+ * scale[m] = absmax/127, q = int8(nearbyint(x * (127/absmax))).  x (M,K) f16/bf16 row stride ldx; q (M,K) int8. */
+int zl_int8_quant_per_token(const void* x, int ldx, void* q, float* scale, int M, int K, int dtype, int pdl,
+                            zl_stream_t stream);
+/* int8_op::layernorm_quant (quant_kernel.cu:106-227): y = RMSNorm(x)*w/scale in T plus the int8 twin q with
+ * qscale[t] = absmax(x*w) * rsqrt / 127. */
+int zl_rmsnorm_quant(const void* x, const void* weight, void* y, void* q, float* qscale, int T, int D, float eps,
+                     float scale, int dtype, int pdl, zl_stream_t stream);
+/* nn::fp8::dynamic_scaled_quant (src/nn/quant/fp8/fp8_util.cu:110-228): *scale = absmax/448 over all n elements,
+ * q = e4m3(sat(x * (1/scale))) with the reference's fp16 product rounding.  n <= 4 Mi elements (decode sizes). */
+int zl_fp8_quant_per_tensor(const void* x, void* q, float* scale, size_t n, int dtype, int pdl, zl_stream_t stream);
+/* Int8Linear::forward GEMM + int8_op::quant_scale_back (+add_bias), or Fp8Linear::forward's scaled fp8 GEMM, as ONE
+ * kernel: y(M,N) = T(acc * x_scale * w_scale) (+bias).  xq (M,K) int8/e4m3; w (N,K) int8/e4m3 row-major (the
+ * reference's parameter layout); kind ZL_W8_INT8: x_scale (M) f32, w_scale (N) of w_scale_dtype (ZL_F32 or dtype);
+ * kind ZL_W8_FP8: both scales one f32.  INT8 results are bit-identical to the reference's three-kernel path. */
+int zl_w8a8_gemm(const void* xq, const float* x_scale, const void* w, const void* w_scale, int w_scale_dtype,
+                 const void* bias, void* y, int M, int N, int K, int kind, int dtype, int pdl, zl_stream_t stream);
+
 /* functions::Gemm / NormalLinear for skinny M (lm_head, bf16 models; src/nn/linear/linear.cpp:150-430,
  * src/nn/embedding/embedding.cu:353-392): y(M,N) = x(M,K) @ W(N,K)^T (+bias), dtype f16/bf16,
  * out_dtype f16/bf16/f32. */
@@ -156,7 +177,8 @@ int zl_add_rmsnorm(const void* a, const void* b, const void* weight, void* out_s
 int zl_element_add_scale(const void* a, const void* b, void* c, size_t n, float scale, int dtype,
                          zl_stream_t stream);
 /* nn::gate_mul_inplace (src/nn/linear/activation_kernel.cu:55-106): out = T(act(float(gate))*float(up));
- * act 0 = silu, 1 = gelu.  gate/up (T, F) with row strides. */
+ * act 0 = silu, 1 = gelu.  gate/up (T, F) with row strides.  up == NULL: out = T(act(gate)), the activation
+ * Linear::activate applies (src/nn/linear/linear.cpp activate(), activation_kernel.cu). */
 int zl_gate_mul(const void* gate, int ld_gate, const void* up, int ld_up, void* out, int ld_out, int T, int F,
                 int act, int dtype, zl_stream_t stream);
 
@@ -187,6 +209,9 @@ int zl_qkv_rope_append(const float* cos, const float* sin, const void* qkv, void
  * Decode attention over per-task ragged KV buffers
  * nn::multi_query_attention_rag_buffer (src/nn/attention/attention_kernel.cu:1252-1457)
  * ------------------------------------------------------------------------------------------ */
+/* one-shot hint: the NEXT zl_decode_attention call on this thread also prefetches [ptr, ptr+bytes) into L2
+ * (weights of a later GEMM; attention leaves HBM idle at small batch). */
+int zl_decode_attention_set_prefetch(const void* ptr, size_t bytes);
 size_t zl_decode_attention_workspace_bytes(int B, int len_q, int num_heads, int dim_head, int max_len_buf);
 /* q (B, len_q, H_q, d); buf_lens (B); k_addrs/v_addrs (B) device arrays of device pointers;
  * mask int8 ragged concat of (len_q, len_buf_b); out (B, len_q, H_q, d).  bshd: (len_buf, H_kv, d) else

@@ -97,6 +97,31 @@ def check_int8(g):
     assert (np.abs(g["allreduce"].astype(np.float32) - ar) > 1e-6).mean() < 5e-3
 
 
+def check_w8(g):
+    c = gc.case_w8()
+    for tag in ("f16", "bf16"):
+        x = ops._t(c["x"], tag)
+        q, sx = ops.int8_quant_per_token(x)
+        np.testing.assert_array_equal(g["q_" + tag], q)                       # integer work: bit-exact
+        np.testing.assert_array_equal(g["sx_" + tag], sx)
+        acc = q.astype(np.int32) @ c["w_q"].astype(np.int32).T
+        np.testing.assert_array_equal(g["acc_" + tag], acc)
+        ws = ops._t(c["w_s"], tag)
+        np.testing.assert_array_equal(g["back_" + tag], ops.int8_scale_back(acc, sx, ws, tag))
+        np.testing.assert_array_equal(g["back_f32scale_" + tag], ops.int8_scale_back(acc, sx, ws, tag))
+        y, lq, ls = ops.rmsnorm_quant(x, ops._t(c["ln_w"], tag), c["eps"], 1.0, tag)
+        np.testing.assert_array_equal(g["ln_q_" + tag], lq)
+        np.testing.assert_allclose(g["ln_s_" + tag], ls, rtol=2e-6)            # device rsqrtf vs exact 1/sqrt
+        assert _rel(g["ln_y_" + tag], y) < (1e-3 if tag == "f16" else 4e-3)
+        fq, fs = ops.fp8_quant_per_tensor(x, dtype=tag)
+        np.testing.assert_array_equal(g["f8_s_" + tag], np.array([fs], np.float32))
+        np.testing.assert_array_equal(ops.e4m3_decode(g["f8_q_" + tag]), fq)   # same e4m3 codes (as values)
+        wv = ops.e4m3_decode(c["w_f8"])
+        for key, bias in (("f8_y_", None), ("f8_y_bias_", ops._t(c["bias"], tag))):
+            yo = ops.fp8_linear(x, wv, c["w_f8_scale"], tag, bias)
+            assert _rel(g[key + tag], yo) < (1e-3 if tag == "f16" else 4e-3), (key, tag, _rel(g[key + tag], yo))
+
+
 CHECKS = {
     "ref_gptq_layout": lambda g: check_layout(g, False),
     "ref_awq_layout": lambda g: check_layout(g, True),
@@ -108,6 +133,7 @@ CHECKS = {
     "ref_attention_short": lambda g: check_attention(g, False),
     "ref_attention_long": lambda g: check_attention(g, True),
     "ref_int8": check_int8,
+    "ref_w8": check_w8,
 }
 
 

@@ -139,12 +139,53 @@ class Ref:
                                                 0 if q.dtype == torch.float16 else 1, algo_id, self.p(out)))
         return out
 
+    def quant_calc_scale_dt(self, x):
+        m, k = x.shape
+        q = torch.empty((m, k), dtype=torch.int8, device=self.dev)
+        s = torch.empty(m, dtype=torch.float32, device=self.dev)
+        self._chk(self.lib.zlref_quant_calc_scale(self.p(x), m, k, 0 if x.dtype == torch.float16 else 1, self.p(q),
+                                                  self.p(s)))
+        return q, s
+
     def quant_calc_scale(self, x):
         m, k = x.shape
         q = torch.empty((m, k), dtype=torch.int8, device=self.dev)
         s = torch.empty(m, dtype=torch.float32, device=self.dev)
         self._chk(self.lib.zlref_quant_calc_scale(self.p(x), m, k, 0, self.p(q), self.p(s)))
         return q, s
+
+    def quant_scale_back(self, acc, sx, sy, dtype):
+        m, n = acc.shape
+        code = {torch.float16: 0, torch.bfloat16: 1, torch.float32: 2}
+        out = torch.empty((m, n), dtype=dtype, device=self.dev)
+        self._chk(self.lib.zlref_quant_scale_back(self.p(acc), self.p(sx), self.p(sy), code[sy.dtype], m, n, code[dtype],
+                                                  self.p(out)))
+        return out
+
+    def layernorm_quant(self, x, w, eps, scale=1.0):
+        t, d = x.shape
+        y = torch.empty_like(x)
+        q = torch.empty((t, d), dtype=torch.int8, device=self.dev)
+        s = torch.empty(t, dtype=torch.float32, device=self.dev)
+        self._chk(self.lib.zlref_layernorm_quant(self.p(x), self.p(w), t, d, ctypes.c_float(eps), ctypes.c_float(scale),
+                                                 0 if x.dtype == torch.float16 else 1, self.p(y), self.p(q), self.p(s)))
+        return y, q, s
+
+    def fp8_quant(self, x):
+        m, k = x.shape
+        q = torch.empty((m, k), dtype=torch.uint8, device=self.dev)
+        s = torch.empty(1, dtype=torch.float32, device=self.dev)
+        self._chk(self.lib.zlref_fp8_dynamic_scaled_quant(self.p(x), m, k, 0 if x.dtype == torch.float16 else 1,
+                                                          self.p(q), self.p(s)))
+        return q, s
+
+    def fp8_gemm(self, xq, sx, wq, sw, bias, dtype):
+        m, k = xq.shape
+        n = wq.shape[0]
+        out = torch.empty((m, n), dtype=dtype, device=self.dev)
+        self._chk(self.lib.zlref_fp8_gemm(self.p(xq), self.p(sx), self.p(wq), self.p(sw), self.p(bias), m, n, k,
+                                          0 if dtype == torch.float16 else 1, self.p(out)))
+        return out
 
     def quant_group_32(self, x):
         m = x.numel() // 32
@@ -247,6 +288,24 @@ def main(out_dir):
     q, s = ref.quant_calc_scale(ref.t(c["x"]))
     np.savez(os.path.join(out_dir, "ref_int8.npz"), q=n(q), s=n(s),
              allreduce=allreduce_int8_with_reference_kernels(ref, c["parts"]))
+    c = gc.case_w8()
+    outs = {}
+    for tag, dt in (("f16", torch.float16), ("bf16", torch.bfloat16)):
+        x = ref.t(c["x"]).to(dt)
+        q, sx = ref.quant_calc_scale_dt(x)
+        acc = (q.cpu().int() @ torch.from_numpy(c["w_q"]).int().T).to(ref.dev)
+        sw = ref.t(c["w_s"]).to(dt)
+        outs["q_" + tag], outs["sx_" + tag], outs["acc_" + tag] = n(q), n(sx), n(acc)
+        outs["back_" + tag] = n(ref.quant_scale_back(acc, sx, sw, dt).float())
+        outs["back_f32scale_" + tag] = n(ref.quant_scale_back(acc, sx, sw.float(), dt).float())
+        y, lq, ls = ref.layernorm_quant(x, ref.t(c["ln_w"]).to(dt), c["eps"])
+        outs["ln_y_" + tag], outs["ln_q_" + tag], outs["ln_s_" + tag] = n(y.float()), n(lq), n(ls)
+        fq, fs = ref.fp8_quant(x)
+        outs["f8_q_" + tag], outs["f8_s_" + tag] = n(fq), n(fs)
+        sw8 = ref.t(np.array([c["w_f8_scale"]], np.float32))
+        outs["f8_y_" + tag] = n(ref.fp8_gemm(fq, fs, ref.t(c["w_f8"]), sw8, None, dt).float())
+        outs["f8_y_bias_" + tag] = n(ref.fp8_gemm(fq, fs, ref.t(c["w_f8"]), sw8, ref.t(c["bias"]).to(dt), dt).float())
+    np.savez(os.path.join(out_dir, "ref_w8.npz"), **outs)
     print("wrote goldens to", out_dir)
 
 

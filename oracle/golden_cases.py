@@ -89,3 +89,18 @@ def case_int8():
     x = r.standard_normal((m, k)).astype(np.float16)
     parts = [r.standard_normal((8, 256)).astype(np.float16) for _ in range(ws)]
     return dict(x=x, parts=parts, WS=ws)
+
+
+def case_w8():
+    """W8A8 Linear pieces: per-token int8 quant + scale-back, layernorm_quant, per-tensor fp8 quant + fp8 GEMM."""
+    r = _rng(127)
+    m, k, n = 5, 512, 96
+    x = (r.standard_normal((m, k)) * 1.7).astype(np.float16)
+    x[3] = 0                                                   # all-zero token: absmax 0
+    ln_w = (1.0 + 0.2 * r.standard_normal(k)).astype(np.float16)
+    w_q = r.integers(-127, 128, size=(n, k)).astype(np.int8)
+    w_s = (0.001 + 0.004 * r.random(n)).astype(np.float16)
+    bias = (0.1 * r.standard_normal(n)).astype(np.float16)
+    w_f8 = r.integers(0, 256, size=(n, k)).astype(np.uint8)
+    w_f8[(w_f8 & 0x7F) == 0x7F] = 0x38                         # no NaN encodings (0x7f / 0xff)
+    return dict(x=x, ln_w=ln_w, eps=1e-5, w_q=w_q, w_s=w_s, bias=bias, w_f8=w_f8, w_f8_scale=np.float32(0.0123))

@@ -200,12 +200,36 @@ def kv_append(k_buf, v_buf, k_new, v_new, placement):
 # INT8 / FP8 activation quantization
 # ----------------------------------------------------------------------------
 def int8_quant_per_token(x):
-    """quant_kernel.cu:15-47: scale = absmax/127 ; q = int8(nearbyint(x * (127/absmax)))."""
+    """quant_kernel.cu:15-47: scale = absmax/127 ; q = int8(nearbyint(x * (127/absmax))).
+    An all-zero row gives 0*inf = NaN, which the device float->int8 conversion turns into 0 (scale 0)."""
     x = np.asarray(x, dtype=F32)
     amax = np.abs(x).max(-1, keepdims=True).astype(F32)
-    bs = F32(127.0) / amax
-    q = np.rint(x * bs).astype(np.int8)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        bs = F32(127.0) / amax
+        r = np.rint(x * bs)
+    q = np.where(np.isnan(r), 0, r).astype(np.int8)
     return q, (amax / F32(127.0)).reshape(-1).astype(F32)
+
+
+def rmsnorm_quant(x, weight, eps, scale=1.0, dtype="f16"):
+    """layernorm_quant / fuse_layernorm_rms_quant (quant_kernel.cu:106-151): returns (y in T as f32, q int8, qscale).
+    absmax of x*w is rounded through T (blockReduceMax<T>), 127.0/absmax is a double division rounded to float,
+    the int8 twin quantises x*w/scale WITHOUT rsqrt and the scale carries rsqrt."""
+    x = np.asarray(x, dtype=F32)
+    w = np.asarray(weight, dtype=F32)
+    d = x.shape[-1]
+    vw = (x * w).astype(F32)
+    amax = _t(np.abs(vw).max(-1, keepdims=True), dtype)
+    rs = (F32(1.0) / np.sqrt((x.astype(np.float64) ** 2).sum(-1, keepdims=True) / d + eps)).astype(F32)
+    with np.errstate(divide="ignore"):
+        bs = (127.0 / amax.astype(np.float64)).astype(F32)
+    v = (vw / F32(scale)).astype(F32)
+    y = _t(v * rs, dtype)
+    with np.errstate(invalid="ignore"):
+        r = np.rint((v * bs).astype(F32))
+    q = np.where(np.isnan(r), 0, r).astype(np.int8)
+    qscale = ((amax * rs).astype(F32).astype(np.float64) / 127.0).astype(F32).reshape(-1)
+    return y, q, qscale
 
 
 def int8_weight_quant_per_row(w):
@@ -219,11 +243,14 @@ def int8_scale_back(acc_i32, scale_x, scale_y, dtype="f16"):
     return _t(acc * np.asarray(scale_x, F32)[:, None] * np.asarray(scale_y, F32)[None, :], dtype)
 
 
-def int8_linear(x, w_q, w_scale, dtype="f16"):
-    """Int8Linear::forward (linear.cpp:560-636): quant -> s32 gemm -> scale back."""
+def int8_linear(x, w_q, w_scale, dtype="f16", bias=None):
+    """Int8Linear::forward (linear.cpp:560-636): quant -> s32 gemm -> scale back (-> add_bias in T, :631-633)."""
     xq, xs = int8_quant_per_token(x)
     acc = xq.astype(np.int32) @ np.asarray(w_q).astype(np.int32).T
-    return int8_scale_back(acc, xs, w_scale, dtype)
+    y = int8_scale_back(acc, xs, w_scale, dtype)
+    if bias is not None:
+        y = _t(y + np.asarray(bias, F32), dtype)
+    return y
 
 
 E4M3_MAX = 448.0
@@ -244,19 +271,39 @@ def e4m3_round(x):
     return (s * np.where(nz, out, 0.0)).astype(F32)
 
 
-def fp8_quant_per_tensor(x, max_e4m3=E4M3_MAX):
-    """fp8_util.cu:110-147,176-228: scale = max|x| / 448 over the whole tensor;
-    q = e4m3(sat(x / scale))."""
+def e4m3_decode(b):
+    """OCP e4m3fn byte -> fp32 value (0x7f/0xff = NaN)."""
+    b = np.asarray(b, dtype=np.uint8).astype(np.int32)
+    sign = np.where(b & 0x80, -1.0, 1.0)
+    e = (b >> 3) & 0xF
+    m = b & 7
+    val = np.where(e == 0, m * 2.0 ** -9, (1.0 + m / 8.0) * np.exp2(e.astype(np.float64) - 7))
+    val = np.where((e == 15) & (m == 7), np.nan, val)
+    return (sign * val).astype(F32)
+
+
+def fp8_quant_per_tensor(x, max_e4m3=E4M3_MAX, dtype="f16"):
+    """fp8_util.cu:110-147,176-228: scale = max|x| / 448 over the whole tensor; q = e4m3_rn_satfinite(h) where
+    h = x_f16 * half(1/scale) rounded in fp16 for fp16 inputs (:77-80) and h = half(float(x) * (1/scale)) for bf16
+    inputs (:74-76).  Returns (values of q as fp32, scale)."""
     x = np.asarray(x, dtype=F32)
-    scale = F32(np.abs(x).max() / F32(max_e4m3))
-    return e4m3_round(x / scale), scale
+    scale = F32(np.abs(x).max()) / F32(max_e4m3)
+    inv = F32(1.0) / scale
+    if dtype == "f16":
+        h = (x.astype(np.float16).astype(F32) * np.float16(inv).astype(F32)).astype(np.float16)
+    else:
+        h = (x * inv).astype(F32).astype(np.float16)
+    return e4m3_round(h.astype(F32)), scale
 
 
-def fp8_linear(x, w_fp8_vals, w_scale, dtype="f16"):
+def fp8_linear(x, w_fp8_vals, w_scale, dtype="f16", bias=None):
     """Fp8Linear::forward (linear.cpp:1660-1695): y = T((xq @ wq^T) * s_x * s_w), fp32 accumulate."""
-    xq, xs = fp8_quant_per_tensor(x)
-    acc = xq.astype(F32) @ np.asarray(w_fp8_vals, dtype=F32).T
-    return _t(acc * xs * F32(w_scale), dtype)
+    xq, xs = fp8_quant_per_tensor(x, dtype=dtype)
+    acc = xq.astype(np.float64) @ np.asarray(w_fp8_vals, dtype=np.float64).T
+    y = acc * np.float64(xs * F32(w_scale))
+    if bias is not None:
+        y = y + np.asarray(bias, dtype=np.float64)
+    return _t(y.astype(F32), dtype)
 
 
 # ----------------------------------------------------------------------------

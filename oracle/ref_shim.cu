@@ -12,6 +12,8 @@
 
 #include "nn/quant/gptq/gptq.h"
 #include "nn/quant/int8/quant_kernel.h"
+#include "nn/quant/fp8/fp8.h"
+#include <bmengine/functions/gemm.h>
 #include "nn/attention/attention_kernel.h"
 #include "nn/layernorm/layernorm.h"
 #include "nn/position/rotary_embedding.h"
@@ -203,6 +205,36 @@ int zlref_mqa_rag_buffer(const void* q, const void* buf_lens, const void* k_addr
 int zlref_quant_calc_scale(const void* x, int M, int K, int dtype, void* out_q, void* out_scale) {
     ZLREF_TRY(Tensor X = wrap({(size_t)M, (size_t)K}, dt_of(dtype), x); Tensor Qo = wrap({(size_t)M, (size_t)K}, DataType::kInt8, out_q);
               Tensor So = wrap({(size_t)M}, DataType::kFloat, out_scale); int8_op::quant_calc_scale(*g_ctx, X, &Qo, &So))
+}
+int zlref_quant_scale_back(const void* acc_i32, const void* sx, const void* sy, int sy_dtype, int M, int N, int dtype,
+                           void* out) {
+    ZLREF_TRY(Tensor A = wrap({(size_t)M, (size_t)N}, DataType::kInt32, acc_i32); Tensor SX = wrap({(size_t)M}, DataType::kFloat, sx);
+              Tensor SY = wrap({(size_t)N}, dt_of(sy_dtype), sy); Tensor O = wrap({(size_t)M, (size_t)N}, dt_of(dtype), out);
+              int8_op::quant_scale_back(*g_ctx, A, &SX, &SY, dt_of(dtype), &O))
+}
+int zlref_layernorm_quant(const void* x, const void* w, int T, int D, float eps, float scale, int dtype, void* out,
+                          void* out_q, void* out_scale) {
+    ZLREF_TRY(DataType dt = dt_of(dtype); Tensor X = wrap({(size_t)T, (size_t)D}, dt, x); Tensor W = wrap({(size_t)D}, dt, w);
+              Tensor O = wrap({(size_t)T, (size_t)D}, dt, out); Tensor Q = wrap({(size_t)T, (size_t)D}, DataType::kInt8, out_q);
+              Tensor S = wrap({(size_t)T}, DataType::kFloat, out_scale); int8_op::layernorm_quant(*g_ctx, X, W, &O, &Q, &S, eps, scale))
+}
+int zlref_fp8_dynamic_scaled_quant(const void* x, int M, int K, int dtype, void* out_q, void* out_scale) {
+    ZLREF_TRY(Tensor X = wrap({(size_t)M, (size_t)K}, dt_of(dtype), x); Tensor q = nn::fp8::dynamic_scaled_quant(*g_ctx, X);
+              copy_out(q, out_q); copy_out(*q.quant_scale, out_scale))
+}
+// Fp8Linear::forward's GEMM (linear.cpp:1675-1680): functions::Gemm(kFP8_E4M3, transA=false, transB=true) with A/B scales
+int zlref_fp8_gemm(const void* xq, const void* sx, const void* wq, const void* sw, const void* bias, int M, int N, int K,
+                   int dtype, void* out) {
+    // Gemm::impl::gemm wants the activation allocation rounded up to 32 rows (gemm.cpp:287), which is how
+    // dynamic_scaled_quant allocates its output (fp8_util.cu:191-192): copy into such a buffer
+    ZLREF_TRY(DataType dt = dt_of(dtype);
+              Tensor A = g_ctx->tensor({(size_t)M, (size_t)K}, DataType::kFP8_E4M3, "", 32 * (size_t)K);
+              BM_CUDART_ASSERT(cudaMemcpyAsync(A.data(), xq, (size_t)M * K, cudaMemcpyDeviceToDevice, g_ctx->current_stream()->ptr));
+              Tensor W = wrap({(size_t)N, (size_t)K}, DataType::kFP8_E4M3, wq); Tensor SA = wrap({1}, DataType::kFloat, sx);
+              Tensor SB = wrap({1}, DataType::kFloat, sw); Tensor B; if (bias) B = wrap({(size_t)N}, dt, bias);
+              functions::Gemm gemm(*g_ctx, DataType::kFP8_E4M3, false, true, 1.f); gemm.set_output_type(dt);
+              gemm.set_A_scale(SA); gemm.set_B_scale(SB); Tensor r = gemm.forward(*g_ctx, A, W, nullptr, bias ? &B : nullptr);
+              copy_out(r, out))
 }
 int zlref_quant_group_32(const void* x, size_t M, int dtype, void* out_q, void* out_scale) {
     ZLREF_TRY(Tensor X = wrap({M, 32}, dt_of(dtype), x); auto r = int8_op::quant_group_32(*g_ctx, X);

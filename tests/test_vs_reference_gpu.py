@@ -127,3 +127,55 @@ def test_decode_attention_vs_reference(lib, ref, cuda, lens):
     out_ref = ref.attention(q, lens_t, ks, vs, mask, d ** -0.5, hkv)
     out = ops.decode_attention(q, lens_t, ks, vs, mask, d ** -0.5, max(lens), hkv)
     assert rel_l2(out.float().cpu().numpy(), out_ref.float().cpu().numpy()) <= 1e-3
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_int8_linear_bit_exact_vs_reference_kernels(lib, ref, cuda, dt):
+    """Int8Linear = quant_calc_scale -> s32 GEMM -> quant_scale_back (linear.cpp:560-636).  The s32 GEMM is exact
+    integer arithmetic (torch int matmul stands in for cuBLASLt); both ends are the reference's own kernels."""
+    from zhilight_b200 import ops
+    m, n, k = 7, 1536, 4096
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(m, k, generator=g) * 1.3).to(dt).to(cuda)
+    w_q = torch.randint(-127, 128, (n, k), generator=g, dtype=torch.int8).to(cuda)
+    w_s = (0.0005 + 0.003 * torch.rand(n, generator=g)).to(dt).to(cuda)
+    r_q, r_s = ref.quant_calc_scale_dt(x)
+    q, s = ops.int8_quant_per_token(x)
+    assert torch.equal(q, r_q) and torch.equal(s, r_s)
+    acc = (r_q.cpu().int() @ w_q.cpu().int().T).to(cuda)
+    y_ref = ref.quant_scale_back(acc, r_s, w_s, dt)
+    y = ops.int8_linear(x, w_q, w_s)
+    assert torch.equal(y, y_ref)
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_rmsnorm_quant_vs_reference(lib, ref, cuda, dt):
+    from zhilight_b200 import ops
+    t, d = 5, 4096
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(t, d, generator=g).to(dt).to(cuda)
+    w = (1 + 0.2 * torch.randn(d, generator=g)).to(dt).to(cuda)
+    ry, rq, rs = ref.layernorm_quant(x, w, 1e-5)
+    y, q, s = ops.rmsnorm_quant(x, w, 1e-5)
+    assert torch.equal(q, rq)
+    torch.testing.assert_close(s, rs, rtol=1e-6, atol=0)
+    assert rel_l2(y.float().cpu().numpy(), ry.float().cpu().numpy()) < 1e-3
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_fp8_linear_vs_reference(lib, ref, cuda, dt):
+    """dynamic_scaled_quant codes must be identical; the GEMM is cuBLASLt fp8 in the reference (fp32 accumulate,
+    different summation order): <= 1e-3 rel."""
+    from zhilight_b200 import ops
+    m, n, k = 8, 2048, 4096
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(m, k, generator=g) * 2).to(dt).to(cuda)
+    w8 = (torch.randn(n, k, generator=g) * 0.5).to(torch.float8_e4m3fn).view(torch.uint8).to(cuda)
+    sw = torch.tensor([0.01], dtype=torch.float32, device=cuda)
+    rq, rs = ref.fp8_quant(x)
+    q, s = ops.fp8_quant_per_tensor(x)
+    assert torch.equal(s, rs)
+    assert torch.equal(q, rq)
+    y_ref = ref.fp8_gemm(rq, rs, w8, sw, None, dt).float().cpu().numpy()
+    y = ops.w8a8_gemm(q, s, w8, sw, dt, kind=ops.W8_FP8).float().cpu().numpy()
+    assert rel_l2(y, y_ref) < (1e-3 if dt == torch.float16 else 4e-3)

@@ -40,7 +40,7 @@ k_decode_attn(const T* __restrict__ q, const int32_t* __restrict__ buf_lens, T* 
               T* const* __restrict__ v_addrs, const int8_t* __restrict__ mask, float scale,
               T* __restrict__ out, float* __restrict__ part_o, float* __restrict__ part_m,
               float* __restrict__ part_l, int len_q, int num_heads, int num_kv_heads, int m_query,
-              int num_splits, int bshd) {
+              int num_splits, int bshd, const uint8_t* __restrict__ pf_ptr, unsigned long long pf_bytes) {
     constexpr int NI = D / 32;                 // 16-byte chunks per lane per key row
     constexpr int DC = D / 8;                  // threads covering one V row
     constexpr int NSUB = kAttnThreads / DC;    // key subsets in the PV phase
@@ -58,6 +58,13 @@ k_decode_attn(const T* __restrict__ q, const int32_t* __restrict__ buf_lens, T* 
     const int head0 = hk * m_query + mq0;
 
     pdl_trigger();
+    // attention barely touches HBM at small batch: use the time to pull a later GEMM's weights into L2
+    if (pf_ptr) {
+        const int n_cta = gridDim.x * gridDim.y * gridDim.z;
+        const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        const int wpc = blockDim.x >> 5;
+        l2_prefetch_lines(pf_ptr, (size_t)pf_bytes, cta * wpc + warp, n_cta * wpc, lane);
+    }
     pdl_wait();
 
     const int len_buf = buf_lens[b];
@@ -230,7 +237,7 @@ k_decode_attn_short(const T* __restrict__ q, const int32_t* __restrict__ buf_len
                     T* const* __restrict__ v_addrs, const int8_t* __restrict__ mask, float scale,
                     T* __restrict__ out, float* __restrict__ part_o, float* __restrict__ part_m,
                     float* __restrict__ part_l, int len_q, int num_heads, int num_kv_heads, int m_query,
-                    int num_splits, int bshd) {
+                    int num_splits, int bshd, const uint8_t* __restrict__ pf_ptr, unsigned long long pf_bytes) {
     constexpr int NI = D / 32;
     constexpr int DC = D / 8;                    // threads per V row
     constexpr int NSUB = kShortThreads / DC;     // 32 (D=128) or 64 (D=64) key subsets
@@ -251,6 +258,13 @@ k_decode_attn_short(const T* __restrict__ q, const int32_t* __restrict__ buf_len
     const int head0 = hk * m_query + mq0;
 
     pdl_trigger();
+    // attention barely touches HBM at small batch: use the time to pull a later GEMM's weights into L2
+    if (pf_ptr) {
+        const int n_cta = gridDim.x * gridDim.y * gridDim.z;
+        const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        const int wpc = blockDim.x >> 5;
+        l2_prefetch_lines(pf_ptr, (size_t)pf_bytes, cta * wpc + warp, n_cta * wpc, lane);
+    }
     pdl_wait();
 
     const int len_buf = buf_lens[b];
@@ -441,6 +455,15 @@ static int attn_num_splits(int B, int len_q, int num_kv_heads, int m_query, int 
 
 using namespace zl;
 
+// one-shot prefetch hint consumed by the next zl_decode_attention call on this thread (set by the decode driver)
+static thread_local const uint8_t* g_attn_pf_ptr = nullptr;
+static thread_local unsigned long long g_attn_pf_bytes = 0;
+extern "C" int zl_decode_attention_set_prefetch(const void* ptr, size_t bytes) {
+    g_attn_pf_ptr = static_cast<const uint8_t*>(ptr);
+    g_attn_pf_bytes = bytes;
+    return ZL_OK;
+}
+
 extern "C" size_t zl_decode_attention_workspace_bytes(int B, int len_q, int num_heads, int dim_head,
                                                       int max_len_buf) {
     if (B <= 0 || len_q <= 0 || num_heads <= 0 || dim_head <= 0) return 0;
@@ -491,11 +514,11 @@ extern "C" int zl_decode_attention(const void* q, const int32_t* buf_lens, void*
         ZL_CHECK_CUDA(launch(k_decode_attn_short<TT, DD>, grid, dim3(kShortThreads), short_smem_bytes<DD>(),    \
                              stream, pdl != 0, (const TT*)q, buf_lens, (TT* const*)k_addrs,                     \
                              (TT* const*)v_addrs, mask, scale, (TT*)out, part_o, part_m, part_l, len_q,         \
-                             num_heads, num_kv_heads, m_query, splits, bshd));                                  \
+                             num_heads, num_kv_heads, m_query, splits, bshd, g_attn_pf_ptr, g_attn_pf_bytes));                                  \
     } else                                                                                                      \
     ZL_CHECK_CUDA(launch(k_decode_attn<TT, DD>, grid, block, 0, stream, pdl != 0, (const TT*)q, buf_lens,       \
                          (TT* const*)k_addrs, (TT* const*)v_addrs, mask, scale, (TT*)out, part_o, part_m,       \
-                         part_l, len_q, num_heads, num_kv_heads, m_query, splits, bshd));                       \
+                         part_l, len_q, num_heads, num_kv_heads, m_query, splits, bshd, g_attn_pf_ptr, g_attn_pf_bytes));                       \
     if (splits > 1)                                                                                             \
         ZL_CHECK_CUDA(launch(k_attn_combine<TT>, dim3((unsigned)vheads), dim3(DD), 0, stream, pdl != 0,         \
                              (const float*)part_o, (const float*)part_m, (const float*)part_l, (TT*)out, splits));
@@ -505,5 +528,7 @@ extern "C" int zl_decode_attention(const void* q, const int32_t* buf_lens, void*
         if (dim_head == 128) { ZL_ATTN_LAUNCH(__nv_bfloat16, 128) } else { ZL_ATTN_LAUNCH(__nv_bfloat16, 64) }
     }
 #undef ZL_ATTN_LAUNCH
+    g_attn_pf_ptr = nullptr;
+    g_attn_pf_bytes = 0;
     return ZL_OK;
 }

@@ -538,6 +538,12 @@ int enqueue_step(zl_llama* m, int B, int len_bucket) {
         if (!(w4 && c.fuse >= 2) && !(skip & 64))
             RCHECK(zl_qkv_rope_append(m->cosb, m->sinb, m->qkv, m->q, m->d_iota, m->d_pos, L.k_addrs, L.v_addrs, B,
                                       m->hq, m->hkv, d, 1, 1, m->d_lens, dt, pdl, st));
+        if (!(skip & 1)) {
+            const void* pfp = nullptr;
+            size_t pfb = 0;
+            prefetch_target(m, l, 1, B, &pfp, &pfb);
+            zl_decode_attention_set_prefetch(pfp, pfb);
+        }
         if (!(skip & 1))
             RCHECK(zl_decode_attention(m->q, m->d_lens, L.k_addrs, L.v_addrs, nullptr, scale, len_bucket, m->ao, B, 1,
                                        m->hq, m->hkv, d, 1, m->attn_ws, m->attn_ws_bytes, dt, pdl, st));

@@ -97,7 +97,7 @@ __global__ void k_gate_mul(const T* __restrict__ gate, int ldg, const T* __restr
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= F) return;
     float gv = to_f32<T>(gate[(size_t)tok * ldg + i]);
-    float uv = to_f32<T>(up[(size_t)tok * ldu + i]);
+    const float uv = up ? to_f32<T>(up[(size_t)tok * ldu + i]) : 1.f;   // up == NULL: plain activation
     float a = act == 0 ? silu_f(gv) : gelu_f(gv);
     out[(size_t)tok * ldo + i] = from_f32<T>(a * uv);
 }
@@ -255,7 +255,7 @@ extern "C" int zl_element_add_scale(const void* a, const void* b, void* c, size_
 
 extern "C" int zl_gate_mul(const void* gate, int ld_gate, const void* up, int ld_up, void* out, int ld_out, int T,
                            int F, int act, int dtype, zl_stream_t stream) {
-    ZL_CHECK_ARG(gate && up && out && T > 0 && F > 0 && (act == 0 || act == 1));
+    ZL_CHECK_ARG(gate && out && T > 0 && F > 0 && (act == 0 || act == 1));
     dim3 grid(cdiv(F, 256), T);
     ZL_DISPATCH_T(dtype, {
         k_gate_mul<scalar_t><<<grid, 256, 0, stream>>>((const scalar_t*)gate, ld_gate, (const scalar_t*)up, ld_up,

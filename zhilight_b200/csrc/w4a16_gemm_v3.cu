@@ -134,8 +134,11 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
             if (s < total) issue_next();
         // software-managed L2: start pulling the weights of a LATER kernel of the chain into the 126 MB L2 now, so
         // that HBM keeps streaming while this kernel and its neighbours sit in their latency-bound phases
-        if (p.pf_ptr) l2_prefetch_share(p.pf_ptr, (size_t)p.pf_bytes, (int)blockIdx.x * WT + warp, (int)gridDim.x * WT);
+        if (p.pf_ptr && !(p.dbg & 4))
+            l2_prefetch_share(p.pf_ptr, (size_t)p.pf_bytes, (int)blockIdx.x * WT + warp, (int)gridDim.x * WT);
     }
+    if (p.pf_ptr && (p.dbg & 4))
+        l2_prefetch_lines(p.pf_ptr, (size_t)p.pf_bytes, (int)blockIdx.x * WT + warp, (int)gridDim.x * WT, lane);
     // staging assignment: group gi -> warp gi % WT.  RMSNorm weights are constants: fetch them before the wait.
     constexpr int kMaxNg = 8;   // groups per warp kept in registers during staging (K <= 8*WT*128)
     uint2 lnw[kMaxNg];

@@ -207,6 +207,59 @@ def dense_gemm_skinny(x, w, bias=None, out_dtype=None, pdl=False):
     return out
 
 
+W8_INT8, W8_FP8 = 0, 1
+
+
+def int8_quant_per_token(x, pdl=False):
+    """int8_op::quant_calc_scale: returns (q int8 (M,K), scale f32 (M))."""
+    m, k = x.shape
+    q = torch.empty((m, k), dtype=torch.int8, device=x.device)
+    scale = torch.empty((m,), dtype=torch.float32, device=x.device)
+    _lib.call("zl_int8_quant_per_token", _p(x), x.stride(0), _p(q), _p(scale), m, k, _dt(x), int(pdl), _stream())
+    return q, scale
+
+
+def rmsnorm_quant(x, weight, eps, scale=1.0, pdl=False):
+    """int8_op::layernorm_quant: returns (y, q int8, qscale f32 (T))."""
+    t, d = x.shape
+    y = torch.empty_like(x)
+    q = torch.empty((t, d), dtype=torch.int8, device=x.device)
+    qs = torch.empty((t,), dtype=torch.float32, device=x.device)
+    _lib.call("zl_rmsnorm_quant", _p(x), _p(weight), _p(y), _p(q), _p(qs), t, d, eps, scale, _dt(x), int(pdl),
+              _stream())
+    return y, q, qs
+
+
+def fp8_quant_per_tensor(x, pdl=False):
+    """nn::fp8::dynamic_scaled_quant: returns (q uint8 holding e4m3 bits, scale f32 (1))."""
+    q = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    scale = torch.empty((1,), dtype=torch.float32, device=x.device)
+    _lib.call("zl_fp8_quant_per_tensor", _p(x), _p(q), _p(scale), x.numel(), _dt(x), int(pdl), _stream())
+    return q, scale
+
+
+def w8a8_gemm(xq, x_scale, w, w_scale, out_dtype, kind=W8_INT8, bias=None, pdl=False):
+    m, k = xq.shape
+    n = w.shape[0]
+    y = torch.empty((m, n), dtype=out_dtype, device=xq.device)
+    ws_dt = 2 if w_scale.dtype == torch.float32 else _dt(w_scale)
+    _lib.call("zl_w8a8_gemm", _p(xq), _p(x_scale), _p(w), _p(w_scale), ws_dt, _p(bias), _p(y), m, n, k, kind,
+              _dt(y), int(pdl), _stream())
+    return y
+
+
+def int8_linear(x, w_q, w_scale, bias=None, pdl=False):
+    """Int8Linear::forward (linear.cpp:560-636) in two launches instead of three."""
+    q, s = int8_quant_per_token(x, pdl)
+    return w8a8_gemm(q, s, w_q, w_scale, x.dtype, W8_INT8, bias, pdl)
+
+
+def fp8_linear(x, w_fp8, w_scale, bias=None, pdl=False):
+    """Fp8Linear::forward (linear.cpp:1660-1695)."""
+    q, s = fp8_quant_per_tensor(x, pdl)
+    return w8a8_gemm(q, s, w_fp8, w_scale, x.dtype, W8_FP8, bias, pdl)
+
+
 def rmsnorm(x, weight, eps, scale=1.0, pdl=False):
     t, d = x.shape
     y = torch.empty_like(x)
@@ -232,9 +285,14 @@ def element_add_scale(a, b, scale=1.0):
 def gate_mul(gate, up, act="silu"):
     t, f = gate.shape
     out = torch.empty((t, f), dtype=gate.dtype, device=gate.device)
-    _lib.call("zl_gate_mul", ctypes.c_void_p(gate.data_ptr()), gate.stride(0), ctypes.c_void_p(up.data_ptr()),
-              up.stride(0), _p(out), f, t, f, 0 if act == "silu" else 1, _dt(gate), _stream())
+    _lib.call("zl_gate_mul", ctypes.c_void_p(gate.data_ptr()), gate.stride(0), _p(up),
+              up.stride(0) if up is not None else 0, _p(out), f, t, f, 0 if act == "silu" else 1, _dt(gate), _stream())
     return out
+
+
+def activation(x, act):
+    """Linear::activate: silu / gelu in fp32, rounded to T."""
+    return gate_mul(x, None, act)
 
 
 def rope_cos_sin(pos, dim_head, theta, llama3=None, neox=True):
