@@ -320,6 +320,9 @@ int zl_llama_step_device(zl_llama_t* m, int B);
 /* read back the device-resident (token, position) state; synchronous. */
 int zl_llama_get_state(zl_llama_t* m, int32_t* tokens_host, int32_t* positions_host, int B);
 int zl_llama_sync(zl_llama_t* m);
+/* debug: (id, globaltimer ns) records of the persistent decode kernel's last launch (ZL_MEGA_TRACE=1 at finalize);
+ * out[0] = record count, then pairs. */
+int zl_llama_mega_trace(zl_llama_t* m, unsigned long long* out, int n_words);
 zl_stream_t zl_llama_stream(zl_llama_t* m);
 /* bytes the step must read from HBM per rank (weights + lm_head + norms), kernel launches per step. */
 int zl_llama_stats(zl_llama_t* m, int B, double* weight_bytes, int* kernels_per_step);

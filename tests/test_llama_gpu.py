@@ -40,7 +40,7 @@ def _run(cfg, quant, dtype, sym=False, use_pdl=True, use_graph=True, steps=6, ti
 
 @pytest.mark.parametrize("cfg", [TINY, TINY128], ids=["d64", "d128-llama3rope"])
 @pytest.mark.parametrize("sym", [False, True])
-@pytest.mark.parametrize("fuse", [0, 1, 2])
+@pytest.mark.parametrize("fuse", [0, 1, 2, 3])
 def test_gptq_decode_matches_oracle(lib, cuda, cfg, sym, fuse):
     for nxt, logits, ref in _run(cfg, 5, "f16", sym=sym, fuse=fuse):
         # north_star: logits within 1e-3 rel for fp16 -- measured as relative L2 over the vocabulary
@@ -100,11 +100,13 @@ def test_device_resident_stepping_matches_host_stepping(lib, cuda):
     np.testing.assert_array_equal(finals[0][1], finals[1][1])
 
 
-def test_long_context_crosses_attention_buckets(lib, cuda):
-    """Graphs are keyed by (batch, attention-length bucket): decode across the 256 -> 512 boundary."""
+@pytest.mark.parametrize("fuse", [2, 3])
+def test_long_context_crosses_attention_buckets(lib, cuda, fuse):
+    """Graphs are keyed by (batch, attention-length bucket): decode across the 256 -> 512 boundary
+    (fuse 3: the persistent kernel switches to split attention + in-kernel combine)."""
     from zhilight_b200.llama import LlamaDecoder
     sd = omodel.make_state_dict(TINY, 5, 128, False, seed=5)
-    dec = LlamaDecoder(quant_type=5, max_batch=1, max_seq=600, **TINY)
+    dec = LlamaDecoder(quant_type=5, max_batch=1, max_seq=600, fuse=fuse, **TINY)
     dec.load_state_dict(sd)
     orc = omodel.OracleLlama(TINY, sd, 5, 128, False, "f16", fuse_norm=True)
     rng = np.random.default_rng(0)
@@ -117,3 +119,34 @@ def test_long_context_crosses_attention_buckets(lib, cuda):
         else:
             orc.decode(toks[p:p + 1], [p])
     dec.close()
+
+
+LAYER8B = dict(num_layers=3, dim_model=4096, num_heads=32, num_kv_heads=8, dim_head=128, dim_ff=14336, vocab_size=2048,
+               eps=1e-5, rope_theta=500000.0, rope_llama3=dict(factor=8.0, low=1.0, high=4.0, orig=8192.0))
+
+
+@pytest.mark.parametrize("cfg,max_batch", [(TINY, 3), (TINY128, 3), (LAYER8B, 2)], ids=["d64", "d128", "llama8b-layers"])
+def test_persistent_kernel_is_bit_identical_to_kernel_chain(lib, cuda, cfg, max_batch):
+    """fuse=3 (one persistent kernel for all layers, grid barriers between phases) performs the same arithmetic in the
+    same order as fuse=2 (kernel per op): logits must be EQUAL, on the toy shapes and on Llama-3.1-8B's real layer
+    shapes (wide qkv / gate_up, tall o / down, all 148 CTAs busy), for changing batch sizes and positions."""
+    from zhilight_b200.llama import LlamaDecoder
+    outs = []
+    for fuse in (2, 3):
+        dec = LlamaDecoder(quant_type=5, group_size=128, sym=True, max_batch=max_batch, max_seq=300, fuse=fuse, **cfg)
+        dec.init_synthetic(seed=11)
+        rng = np.random.default_rng(3)
+        pos = np.zeros(max_batch, np.int32)
+        res = []
+        for s in range(10):
+            b = max_batch if s % 3 != 2 else 1
+            tok = rng.integers(0, cfg["vocab_size"], size=b).astype(np.int32)
+            nxt, logits = dec.decode(tok, pos[:b], want_logits=True)
+            res.append((nxt.copy(), logits.copy()))
+            pos[:b] += 1
+        dec.close()
+        outs.append(res)
+    for (n2, l2), (n3, l3) in zip(*outs):
+        assert np.isfinite(l2).all()
+        np.testing.assert_array_equal(l2, l3)
+        np.testing.assert_array_equal(n2, n3)

@@ -11,6 +11,7 @@
 // P.V runs in fp32 on the CUDA cores with 16-byte coalesced V loads (each V element feeds all heads).
 // Splits are merged with the reference's LSE rule (attention_kernel.cu:881-923).
 #include "common.cuh"
+#include "decode_attn_short.cuh"
 
 namespace zl {
 
@@ -19,20 +20,6 @@ constexpr int kAttnWarps = 4;
 constexpr int kAttnMaxRange = 1024;            // keys per CTA; logits live in shared memory
 constexpr int kAttnRowStride = kAttnMaxRange + 4;
 constexpr int kAttnMaxSplits = 64;
-
-__host__ __device__ inline int attn_round16(int v) { return (v + 15) & ~15; }
-
-template <typename T>
-__device__ __forceinline__ void mma_attn(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
-template <>
-__device__ __forceinline__ void mma_attn<__half>(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    mma_16816_f16(d, a, b0, b1, d);
-}
-template <>
-__device__ __forceinline__ void mma_attn<__nv_bfloat16>(float (&d)[4], const uint32_t (&a)[4], uint32_t b0,
-                                                        uint32_t b1) {
-    mma_16816_bf16(d, a, b0, b1, d);
-}
 
 template <typename T, int D>
 __global__ void __launch_bounds__(kAttnThreads)
@@ -226,11 +213,6 @@ k_decode_attn(const T* __restrict__ q, const int32_t* __restrict__ buf_lens, T* 
 // its V rows) is issued before the first dependent instruction, so the whole CTA costs one memory round trip
 // instead of one per loop iteration.  Same math and split/combine contract as k_decode_attn.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kShortThreads = 512;
-constexpr int kShortWarps = 16;
-constexpr int kShortRange = 256;
-constexpr int kShortRowStride = kShortRange + 4;
-
 template <typename T, int D>
 __global__ void __launch_bounds__(kShortThreads)
 k_decode_attn_short(const T* __restrict__ q, const int32_t* __restrict__ buf_lens, T* const* __restrict__ k_addrs,
@@ -238,25 +220,8 @@ k_decode_attn_short(const T* __restrict__ q, const int32_t* __restrict__ buf_len
                     T* __restrict__ out, float* __restrict__ part_o, float* __restrict__ part_m,
                     float* __restrict__ part_l, int len_q, int num_heads, int num_kv_heads, int m_query,
                     int num_splits, int bshd, const uint8_t* __restrict__ pf_ptr, unsigned long long pf_bytes) {
-    constexpr int NI = D / 32;
-    constexpr int DC = D / 8;                    // threads per V row
-    constexpr int NSUB = kShortThreads / DC;     // 32 (D=128) or 64 (D=64) key subsets
-    constexpr int VU = kShortRange / NSUB;       // V rows per thread: 8 or 4
     extern __shared__ __align__(16) float s_dyn[];
-    float* s_logit = s_dyn;                                  // [8][kShortRowStride]
-    float* s_red = s_dyn + 8 * kShortRowStride;              // [16 warps][8 heads][D]
-    __shared__ float s_m[8], s_l[8];
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, t = lane & 3;
-    const int hgroups = (m_query + 7) / 8;
-    const int split = blockIdx.x;
-    const int hk = blockIdx.y / hgroups, hg = blockIdx.y % hgroups;
-    const int bq = blockIdx.z, b = bq / len_q, qi = bq % len_q;
-    const int mq0 = hg * 8;
-    const int mq = min(8, m_query - mq0);
-    const int head0 = hk * m_query + mq0;
-
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_trigger();
     // attention barely touches HBM at small batch: use the time to pull a later GEMM's weights into L2
     if (pf_ptr) {
@@ -266,156 +231,11 @@ k_decode_attn_short(const T* __restrict__ q, const int32_t* __restrict__ buf_len
         l2_prefetch_lines(pf_ptr, (size_t)pf_bytes, cta * wpc + warp, n_cta * wpc, lane);
     }
     pdl_wait();
-
-    const int len_buf = buf_lens[b];
-    const int chunk = attn_round16((len_buf + num_splits - 1) / num_splits);   // host guarantees <= 256
-    const int k0 = split * chunk;
-    const int k1 = min(len_buf, k0 + chunk);
-    const int n = max(0, k1 - k0);
-
-    const size_t stride = bshd ? (size_t)num_kv_heads * D : (size_t)D;
-    const size_t base = bshd ? (size_t)hk * D : (size_t)hk * len_buf * D;
-    const T* kbase = k_addrs[b] + base;
-    const T* vbase = v_addrs[b] + base;
-    const int8_t* mrow = nullptr;
-    if (mask) {
-        size_t len_off = 0;
-        for (int j = 0; j < b; ++j) len_off += buf_lens[j];
-        mrow = mask + (size_t)len_q * len_off + (size_t)qi * len_buf;
-    }
-
-    // ---- issue every load of this CTA up front ----
-    uint4 qf[NI], ka[NI], kb[NI];
-    const int ntiles = (n + 15) >> 4;            // <= 16 == number of warps
-    const bool has_tile = warp < ntiles;
-    const int ka_i = k0 + warp * 16 + g, kb_i = ka_i + 8;
-#pragma unroll
-    for (int i = 0; i < NI; ++i)
-        qf[i] = (g < mq) ? ld_cg_u4(q + ((size_t)bq * num_heads + head0 + g) * D + i * 32 + t * 8) : make_uint4(0, 0, 0, 0);
-    if (has_tile) {
-        const T* pa = kbase + (size_t)min(ka_i, k1 - 1) * stride + t * 8;
-        const T* pb = kbase + (size_t)min(kb_i, k1 - 1) * stride + t * 8;
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-            ka[i] = ld_cg_u4(pa + i * 32);
-            kb[i] = ld_cg_u4(pb + i * 32);
-        }
-    }
-    const int dc = tid % DC, sub = tid / DC;
-    uint4 vv[VU];
-    const T* vp = vbase + (size_t)k0 * stride + dc * 8;
-#pragma unroll
-    for (int u = 0; u < VU; ++u) {
-        const int kk = sub + u * NSUB;
-        if (kk < n) vv[u] = ld_cg_u4(vp + (size_t)kk * stride);
-    }
-
-    // ---- S = K.Q^T ----
-    if (has_tile) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-            const uint32_t a0[4] = {ka[i].x, kb[i].x, ka[i].y, kb[i].y};
-            const uint32_t a1[4] = {ka[i].z, kb[i].z, ka[i].w, kb[i].w};
-            mma_attn<T>(acc, a0, qf[i].x, qf[i].y);
-            mma_attn<T>(acc, a1, qf[i].z, qf[i].w);
-        }
-        const bool va = ka_i < k1 && (!mrow || mrow[ka_i] != 0);
-        const bool vb = kb_i < k1 && (!mrow || mrow[kb_i] != 0);
-        const int la = warp * 16 + g;
-        const float ninf = -INFINITY;
-        if (2 * t < mq) {
-            s_logit[(2 * t) * kShortRowStride + la] = va ? acc[0] * scale : ninf;
-            s_logit[(2 * t) * kShortRowStride + la + 8] = vb ? acc[2] * scale : ninf;
-        }
-        if (2 * t + 1 < mq) {
-            s_logit[(2 * t + 1) * kShortRowStride + la] = va ? acc[1] * scale : ninf;
-            s_logit[(2 * t + 1) * kShortRowStride + la + 8] = vb ? acc[3] * scale : ninf;
-        }
-    }
-    __syncthreads();
-
-    // ---- masked softmax statistics, one warp per head ----
-    if (warp < mq) {
-        float* row = s_logit + warp * kShortRowStride;
-        float mx = -1e20f;
-        for (int i = lane; i < n; i += 32) mx = fmaxf(mx, row[i]);
-        mx = warp_max(mx);
-        float sum = 0.f;
-        for (int i = lane; i < n; i += 32) {
-            const float e = expf(row[i] - mx);
-            row[i] = e;
-            sum += e;
-        }
-        sum = warp_sum(sum) + 1e-20f;
-        if (lane == 0) {
-            s_m[warp] = mx;
-            s_l[warp] = sum;
-        }
-    }
-    __syncthreads();
-
-    // ---- O = P.V from the registers loaded at the top ----
-    float o[8][8];
-#pragma unroll
-    for (int h = 0; h < 8; ++h)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[h][i] = 0.f;
-#pragma unroll
-    for (int u = 0; u < VU; ++u) {
-        const int kk = sub + u * NSUB;
-        if (kk < n) {
-            float vf[8];
-            unpack8<T>(vv[u], vf);
-#pragma unroll
-            for (int h = 0; h < 8; ++h) {
-                if (h < mq) {
-                    const float p = s_logit[h * kShortRowStride + kk];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) o[h][i] = fmaf(p, vf[i], o[h][i]);
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int h = 0; h < 8; ++h)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float v = o[h][i];
-#pragma unroll
-            for (int off = DC; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-            o[h][i] = v;
-        }
-    if (lane < DC) {
-#pragma unroll
-        for (int h = 0; h < 8; ++h)
-            if (h < mq) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) s_red[(warp * 8 + h) * D + lane * 8 + i] = o[h][i];
-            }
-    }
-    __syncthreads();
-    for (int e = tid; e < mq * D; e += kShortThreads) {
-        const int h = e / D, d = e % D;
-        float v = 0.f;
-#pragma unroll
-        for (int w = 0; w < kShortWarps; ++w) v += s_red[(w * 8 + h) * D + d];
-        v = v / s_l[h];
-        const size_t vh = (size_t)bq * num_heads + head0 + h;
-        if (num_splits == 1) {
-            out[vh * D + d] = from_f32<T>(v);
-        } else {
-            part_o[(vh * num_splits + split) * D + d] = v;
-            if (d == 0) {
-                part_m[vh * num_splits + split] = s_m[h];
-                part_l[vh * num_splits + split] = s_l[h];
-            }
-        }
-    }
+    attn_short_item<T, D>(q, buf_lens, k_addrs, v_addrs, mask, scale, out, part_o, part_m, part_l, len_q, num_heads,
+                          num_kv_heads, m_query, num_splits, bshd, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z,
+                          s_dyn);
 }
 
-template <int D>
-constexpr int short_smem_bytes() { return (8 * kShortRowStride + kShortWarps * 8 * D) * (int)sizeof(float); }
 
 // grid (B*len_q*num_heads), block D
 template <typename T>

@@ -7,6 +7,7 @@
 // layer with no graph; here a layer is 8 launches chained with programmatic dependent launch inside one
 // CUDA graph per batch size.
 #include "common.cuh"
+#include "mega_params.h"
 #include "w4_layout.cuh"
 
 #include <cstdlib>
@@ -77,6 +78,11 @@ struct zl_llama {
     int cur_max_len = 0;                            // host-side upper bound of buf_lens (positions + 1)
     double weight_bytes = 0;
     int kernels_per_step = 0;
+    // persistent whole-model kernel (cfg.fuse >= 3): per-layer descriptors, grid-barrier words, debug trace
+    zl::MegaLayer* d_mega_layers = nullptr;
+    unsigned* d_mega_sync = nullptr;        // [0] barrier counter (zeroed every step), [1] sticky abort flag
+    unsigned long long* d_mega_trace = nullptr;
+    bool mega_used = false;
 };
 
 namespace {
@@ -389,7 +395,7 @@ int alloc_runtime(zl_llama* m) {
     m->attn_ws_bytes = zl_decode_attention_workspace_bytes(B, 1, m->hq, d, c.max_seq);
     RCHECK(dmalloc(&m->attn_ws, m->attn_ws_bytes));
     RCHECK(dmalloc(&m->argmax_ws, zl_argmax_workspace_bytes(B)));
-    ZL_CHECK_CUDA(cudaMallocHost((void**)&m->h_stage, sizeof(int32_t) * 4 * B));
+    ZL_CHECK_CUDA(cudaMallocHost((void**)&m->h_stage, sizeof(int32_t) * (4 * B + 4)));
     ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
     return ZL_OK;
 }
@@ -482,6 +488,99 @@ int w4_gemm(zl_llama* m, const void* x, int ldx, const W4Lin& w, const void* res
     return zl_w4a16_gemm_fused(&a, m->stream);
 }
 
+int build_mega_layers(zl_llama* m) {
+    const auto& c = m->cfg;
+    if (!(c.quant_type == 5 || c.quant_type == 6)) return ZL_OK;
+    std::vector<MegaLayer> host(c.num_layers);
+    for (int l = 0; l < c.num_layers; ++l) {
+        Layer& L = m->layers[l];
+        const W4Lin* lin[4] = {&L.q_qkv, &L.q_o, &L.q_gu, &L.q_down};
+        for (int i = 0; i < 4; ++i) {
+            if (!lin[i]->packed_i) return ZL_OK;   // some GEMM has no integer layout: the persistent kernel is not used
+            host[l].packed[i] = static_cast<const uint8_t*>(lin[i]->packed_i);
+            host[l].bias[i] = static_cast<const __half*>(lin[i]->bias);
+        }
+        host[l].ln_attn = static_cast<const __half*>(L.ln_attn);
+        host[l].ln_ff = static_cast<const __half*>(L.ln_ff);
+        host[l].k_addrs = reinterpret_cast<__half* const*>(L.k_addrs);
+        host[l].v_addrs = reinterpret_cast<__half* const*>(L.v_addrs);
+    }
+    RCHECK(dmalloc((void**)&m->d_mega_layers, host.size() * sizeof(MegaLayer)));
+    ZL_CHECK_CUDA(cudaMemcpy(m->d_mega_layers, host.data(), host.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice));
+    RCHECK(dmalloc((void**)&m->d_mega_sync, 16));
+    ZL_CHECK_CUDA(cudaMemset(m->d_mega_sync, 0, 16));
+    if (getenv("ZL_MEGA_TRACE")) {
+        RCHECK(dmalloc((void**)&m->d_mega_trace, 512 * 8));
+        ZL_CHECK_CUDA(cudaMemset(m->d_mega_trace, 0, 512 * 8));
+    }
+    return ZL_OK;
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// fills the parameter block of the persistent kernel; stages = 0 when this (B, bucket) cannot use it
+int mega_plan(zl_llama* m, int B, int len_bucket, MegaParams* p) {
+    const auto& c = m->cfg;
+    if (!m->d_mega_layers || c.tp_size > 1 || c.dtype != ZL_F16 || B > 8 || getenv("ZL_NO_MEGA")) return 0;
+    if (!(c.dim_head == 64 || c.dim_head == 128)) return 0;
+    const int splits = (len_bucket + 255) / 256;
+    const int hgroups = (m->hq / m->hkv + 7) / 8;
+    if (splits > 64 || (long long)B * m->hkv * hgroups * splits > 16LL * num_sms()) return 0;
+    MegaParams q{};
+    q.layers = m->d_mega_layers;
+    q.num_layers = c.num_layers;
+    q.mc = B;
+    const int d = c.dim_head;
+    const int N[4] = {(m->hq + 2 * m->hkv) * d, c.dim_model, 2 * m->ff, c.dim_model};
+    const int K[4] = {c.dim_model, m->hq * d, c.dim_model, m->ff};
+    int k_max = 0;
+    for (int i = 0; i < 4; ++i) {
+        q.gN[i] = N[i];
+        q.gK[i] = K[i];
+        q.gTall[i] = (N[i] / 32 <= num_sms() && K[i] / kW4GroupK >= 32) ? 1 : 0;   // same rule as the per-GEMM kernel
+        if (K[i] % kW4GroupK != 0 || N[i] % 32 != 0 || K[i] / kW4GroupK > 128) return 0;
+        k_max = K[i] > k_max ? K[i] : k_max;
+    }
+    q.num_heads = m->hq;
+    q.num_kv_heads = m->hkv;
+    q.dim_head = d;
+    q.eps = c.eps;
+    q.attn_scale = 1.0f / sqrtf((float)d);
+    q.h = static_cast<__half*>(m->h);
+    q.q = static_cast<__half*>(m->q);
+    q.ao = static_cast<__half*>(m->ao);
+    q.act = static_cast<__half*>(m->act);
+    q.cos = m->cosb;
+    q.sin = m->sinb;
+    q.token_batch = m->d_iota;
+    q.placement = m->d_pos;
+    q.buf_lens = m->d_lens;
+    q.attn_splits = splits;
+    if (splits > 1) {
+        const size_t vheads = (size_t)B * m->hq;
+        if (vheads * splits * (d + 2) * sizeof(float) > m->attn_ws_bytes) return 0;
+        q.part_o = static_cast<float*>(m->attn_ws);
+        q.part_m = q.part_o + vheads * splits * d;
+        q.part_l = q.part_m + vheads * splits;
+    }
+    q.sync = m->d_mega_sync;
+    q.trace = m->d_mega_trace;
+    int stages = 0;
+    if (mega_smem_bytes(B, k_max, d, 4) <= 232448) stages = 4;
+    else if (mega_smem_bytes(B, k_max, d, 3) <= 232448) stages = 3;
+    *p = q;
+    return stages;
+}
+
 // ZL_DEBUG_SKIP (bit mask, timing experiments only -- results are wrong when set):
 // 1 attention, 2 qkv GEMM, 4 o GEMM, 8 gate/up GEMM, 16 down GEMM, 32 lm_head, 64 rope/append kernel
 static int debug_skip() {
@@ -506,12 +605,18 @@ int enqueue_step(zl_llama* m, int B, int len_bucket) {
     }
     const float scale = 1.0f / sqrtf((float)d);   // attention.cpp:89
 
+    // grid-barrier counter of the persistent kernel: zeroed first so that the kernel chain below stays kernel->kernel
+    if (m->d_mega_sync) ZL_CHECK_CUDA(cudaMemsetAsync(m->d_mega_sync, 0, 4, st));
     ZL_CHECK_CUDA(launch(k_lens_from_pos, dim3(cdiv(B, 64)), dim3(64), 0, st, false, (const int32_t*)m->d_pos,
                          m->d_lens, B));
     RCHECK(zl_rope_cos_sin(m->d_pos, m->cosb, m->sinb, B, d, c.rope_theta, c.rope_llama3_factor,
                            c.rope_low_freq_factor, c.rope_high_freq_factor, c.rope_orig_ctx, 1, st));
     RCHECK(zl_embedding(m->d_tokens, m->emb, m->h, B, D, c.vocab_size, dt, 0, st));
-    for (int l = 0; l < c.num_layers; ++l) {
+    MegaParams mp;
+    const int mega_stages = (w4 && c.fuse >= 3 && !skip) ? mega_plan(m, B, len_bucket, &mp) : 0;
+    m->mega_used = mega_stages != 0;
+    if (mega_stages) ZL_CHECK_CUDA(launch_llama_mega(mp, mega_stages, pdl != 0, st));
+    for (int l = 0; l < (mega_stages ? 0 : c.num_layers); ++l) {
         Layer& L = m->layers[l];
         if (w4) {
             const void* xin = m->xn;
@@ -654,7 +759,7 @@ extern "C" int zl_llama_create(const zl_llama_config_t* cfg, zl_llama_t** out) {
     ZL_CHECK_SUPPORTED(cfg->num_heads % cfg->tp_size == 0 && cfg->num_kv_heads % cfg->tp_size == 0 &&
                        cfg->dim_ff % cfg->tp_size == 0 && cfg->vocab_size % cfg->tp_size == 0);
     ZL_CHECK_SUPPORTED(cfg->quant_type == 0 || cfg->group_size == zl::kW4GroupK);
-    ZL_CHECK_ARG(cfg->fuse >= 0 && cfg->fuse <= 2);
+    ZL_CHECK_ARG(cfg->fuse >= 0 && cfg->fuse <= 3);
     ZL_CHECK_SUPPORTED(cfg->fuse < 2 || cfg->dim_head % 32 == 0);
     RCHECK(zl_prepare());
     zl_llama* m = new zl_llama();
@@ -693,7 +798,8 @@ extern "C" void zl_llama_destroy(zl_llama_t* m) {
     }
     for (void* p : {m->emb, m->lm_head_tied ? nullptr : m->lm_head, m->ln_f, m->h, m->xn, m->qkv, m->q, m->ao, m->act,
                     m->pend, m->gu, (void*)m->logits, (void*)m->cosb, (void*)m->sinb, (void*)m->d_tokens,
-                    (void*)m->d_pos, (void*)m->d_lens, (void*)m->d_next, (void*)m->d_iota, m->attn_ws, m->argmax_ws})
+                    (void*)m->d_pos, (void*)m->d_lens, (void*)m->d_next, (void*)m->d_iota, m->attn_ws, m->argmax_ws, (void*)m->d_mega_layers, (void*)m->d_mega_sync,
+                    (void*)m->d_mega_trace})
         if (p) cudaFree(p);
     if (m->h_stage) cudaFreeHost(m->h_stage);
     cudaStreamDestroy(m->stream);
@@ -727,6 +833,7 @@ extern "C" int zl_llama_finalize(zl_llama_t* m) {
         if (!m->layers[l].ln_attn) RCHECK(finalize_layer(m, l));
     RCHECK(finalize_globals(m));
     RCHECK(alloc_runtime(m));
+    RCHECK(build_mega_layers(m));
     m->finalized = true;
     return ZL_OK;
 }
@@ -840,7 +947,15 @@ extern "C" int zl_llama_decode(zl_llama_t* m, const int32_t* tokens_host, const 
     if (logits_host)   // (B, vocab/tp) of this rank's shard
         ZL_CHECK_CUDA(cudaMemcpyAsync(logits_host, m->logits, (size_t)B * m->vshard * 4, cudaMemcpyDeviceToHost,
                                       m->stream));
+    const int mb = m->cfg.max_batch;
+    m->h_stage[4 * mb] = 0;
+    if (m->mega_used)   // sticky abort flag of the persistent kernel travels with the result
+        ZL_CHECK_CUDA(cudaMemcpyAsync(m->h_stage + 4 * mb, m->d_mega_sync + 1, 4, cudaMemcpyDeviceToHost, m->stream));
     ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->h_stage[4 * mb] != 0) {
+        zl_set_last_error(__FILE__, __LINE__, "persistent decode kernel aborted: a grid barrier timed out");
+        return ZL_ERR_STATE;
+    }
     for (int i = 0; i < B; ++i) next_tokens_host[i] = m->h_stage[3 * B + i];
     return ZL_OK;
 }
@@ -913,6 +1028,25 @@ extern "C" int zl_llama_bench_gemms(zl_llama_t* m, int B, int iters, float* ms, 
 extern "C" int zl_llama_sync(zl_llama_t* m) {
     ZL_CHECK_ARG(m);
     ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->d_mega_sync) {
+        unsigned words[2] = {0, 0};
+        ZL_CHECK_CUDA(cudaMemcpy(words, m->d_mega_sync, 8, cudaMemcpyDeviceToHost));
+        if (words[1]) {
+            zl_set_last_error(__FILE__, __LINE__, "persistent decode kernel aborted: a grid barrier timed out");
+            return ZL_ERR_STATE;
+        }
+    }
+    return ZL_OK;
+}
+
+extern "C" int zl_llama_mega_trace(zl_llama_t* m, unsigned long long* out, int n_words) {
+    ZL_CHECK_ARG(m && out && n_words > 0 && n_words <= 512);
+    if (!m->d_mega_trace) {
+        zl_set_last_error(__FILE__, __LINE__, "no trace buffer: set ZL_MEGA_TRACE=1 before zl_llama_finalize");
+        return ZL_ERR_STATE;
+    }
+    ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+    ZL_CHECK_CUDA(cudaMemcpy(out, m->d_mega_trace, (size_t)n_words * 8, cudaMemcpyDeviceToHost));
     return ZL_OK;
 }
 

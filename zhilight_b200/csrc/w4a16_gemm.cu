@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "w4_layout.cuh"
 #include "w4_params.h"
+#include "mega_params.h"
 
 #include <cstdlib>
 
@@ -249,6 +250,7 @@ extern "C" int zl_prepare(void) {
     ZL_CHECK_CUDA(cudaFuncSetAttribute(k_w4a16_mma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kW4SmemBytes));
     ZL_CHECK_CUDA(prepare_w4_v2());
     ZL_CHECK_CUDA(prepare_w4_v3());
+    ZL_CHECK_CUDA(prepare_llama_mega());
     return ZL_OK;
 }
 

@@ -41,12 +41,14 @@ __device__ __forceinline__ void imma_u8u8(int (&d)[4], const uint32_t (&a)[4], u
 // reduction), while the integer decomposition of the activations is staged ONCE per CTA by all warps together:
 //   wide : SUBS=2 x 8 warps, 5-stage rings  (N/32 > #SMs: qkv, gate/up)  -- two tile pipelines per SM
 //   tall : SUBS=1 x 16 warps, 4-stage rings (N/32 <= #SMs: o_proj, down) -- k split 16 ways
-template <int NT, int WARPS, int SUBS, int STAGES>
+// RT = token rows kept in the split-k reduction buffers (even, >= mc): small batches shrink them to make room for
+// deeper rings -- the tile loop is latency-bound on ring depth (4 -> 5 stages is worth ~25 %).
+template <int NT, int WARPS, int SUBS, int STAGES, int RT = NT * 8>
 struct V3Smem {
     static constexpr int kWarpsTotal = WARPS * SUBS;
     static constexpr int kRingBytes = kWarpsTotal * STAGES * kW4BlockBytes;
     static constexpr int kRedBufs = (NT == 1) ? 2 : 1;
-    static constexpr int kRedFloats = WARPS * NT * 8 * 32;                 // per sub-CTA, per buffer
+    static constexpr int kRedFloats = WARPS * RT * 32;                     // per sub-CTA, per buffer
     static constexpr int kBarOff = kRingBytes;
     static constexpr int kRedOff = kBarOff + kWarpsTotal * STAGES * 8;
     static constexpr int kSsOff = kRedOff + SUBS * kRedBufs * kRedFloats * 4;   // [warps total][NT*8]
@@ -64,9 +66,9 @@ __device__ __forceinline__ void sub_barrier(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int NT, bool NORM, int WARPS, int SUBS, int STAGES>
+template <int NT, bool NORM, int WARPS, int SUBS, int STAGES, int RT = NT * 8>
 __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Params p) {
-    using S = V3Smem<NT, WARPS, SUBS, STAGES>;
+    using S = V3Smem<NT, WARPS, SUBS, STAGES, RT>;
     constexpr int WT = WARPS * SUBS;
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -322,24 +324,26 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
 
         // ---- split-k reduction across the warps of this sub-CTA + epilogue ----
         float* rbuf = red + (S::kRedBufs == 2 ? (ti & 1) * S::kRedFloats : 0);
-        float* myred = rbuf + wl * (NT * 8 * 32);
+        float* myred = rbuf + wl * (RT * 32);
 #pragma unroll
         for (int tt = 0; tt < 2; ++tt)
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
                 const int tok = nt * 8 + 2 * t;
                 const int row = tt * 16 + g;
-                myred[tok * 32 + row] = acc[tt][nt][0];
-                myred[(tok + 1) * 32 + row] = acc[tt][nt][1];
-                myred[tok * 32 + row + 8] = acc[tt][nt][2];
-                myred[(tok + 1) * 32 + row + 8] = acc[tt][nt][3];
+                if (RT == NT * 8 || tok < RT) {
+                    myred[tok * 32 + row] = acc[tt][nt][0];
+                    myred[(tok + 1) * 32 + row] = acc[tt][nt][1];
+                    myred[tok * 32 + row + 8] = acc[tt][nt][2];
+                    myred[(tok + 1) * 32 + row + 8] = acc[tt][nt][3];
+                }
             }
         sub_barrier(1 + sub, WARPS * 32);
 
         auto sum_red = [&](int idx) {
             float v = 0.f;
 #pragma unroll
-            for (int w = 0; w < WARPS; ++w) v += rbuf[w * (NT * 8 * 32) + idx];
+            for (int w = 0; w < WARPS; ++w) v += rbuf[w * (RT * 32) + idx];
             return v;
         };
         const int n0 = st * 32;
@@ -439,23 +443,34 @@ static int v3_num_sms() {
 
 constexpr int kV3Budget = 231000;   // one CTA per SM (227 KB usable + 1 KB reserved)
 
-template <int NT, bool NORM, int WARPS, int SUBS, int STAGES>
+template <int NT, bool NORM, int WARPS, int SUBS, int STAGES, int RT>
 static cudaError_t launch_v3_t(const W4Params& p, int smem, bool pdl, cudaStream_t stream) {
     const int tiles = p.N / 32;
     const int want = (tiles + SUBS - 1) / SUBS;
     const int grid = want < v3_num_sms() ? want : v3_num_sms();
-    return launch(k_w4a16_v3<NT, NORM, WARPS, SUBS, STAGES>, dim3(grid), dim3(WARPS * SUBS * 32), (size_t)smem, stream,
+    return launch(k_w4a16_v3<NT, NORM, WARPS, SUBS, STAGES, RT>, dim3(grid), dim3(WARPS * SUBS * 32), (size_t)smem, stream,
                   pdl, p);
 }
 
-template <int NT, int WARPS, int SUBS, int STAGES>
+template <int NT, int WARPS, int SUBS, int STAGES, int RT = NT * 8>
 static bool v3_try(const W4Params& p, bool pdl, cudaStream_t stream, cudaError_t* err) {
     const int G = p.K / kW4GroupK;
-    const int smem = V3Smem<NT, WARPS, SUBS, STAGES>::kBytes + v3_stage_bytes(p.mc, p.K);
-    if (G > 8 * WARPS * SUBS || smem > kV3Budget) return false;   // 8 = kMaxNg
-    *err = p.ln_w ? launch_v3_t<NT, true, WARPS, SUBS, STAGES>(p, smem, pdl, stream)
-                  : launch_v3_t<NT, false, WARPS, SUBS, STAGES>(p, smem, pdl, stream);
+    const int smem = V3Smem<NT, WARPS, SUBS, STAGES, RT>::kBytes + v3_stage_bytes(p.mc, p.K);
+    if (G > 8 * WARPS * SUBS || smem > kV3Budget || p.mc > RT) return false;   // 8 = kMaxNg
+    *err = p.ln_w ? launch_v3_t<NT, true, WARPS, SUBS, STAGES, RT>(p, smem, pdl, stream)
+                  : launch_v3_t<NT, false, WARPS, SUBS, STAGES, RT>(p, smem, pdl, stream);
     return true;
+}
+
+static int v3_max_stages() {
+    static int v = -1;
+    if (v < 0) {
+        // measured on B200 (Llama-3.1-8B B=1): 5 stages 600 tok/s, 6 stages 568 tok/s -- deeper rings only add HBM
+        // queueing, so the 6-stage variants stay opt-in
+        const char* e = getenv("ZL_W4_STAGES");
+        v = e ? atoi(e) : 4;
+    }
+    return v;
 }
 
 static bool v3_is_tall(const W4Params& p) {
@@ -472,6 +487,15 @@ static bool v3_is_tall(const W4Params& p) {
 // returns false when the staged activations do not fit shared memory (caller falls back to the fp16 kernels)
 bool launch_w4_v3(const W4Params& p, bool pdl, cudaStream_t stream, cudaError_t* err) {
     const bool tall = v3_is_tall(p);
+    if (p.mc <= 2) {   // deepest ring that fits (reduction buffers shrunk to 2 token rows)
+        const int ms = v3_max_stages();
+        if (tall) {
+            if (ms >= 6 && v3_try<1, 16, 1, 6, 2>(p, pdl, stream, err)) return true;
+            if (ms >= 5 && v3_try<1, 16, 1, 5, 2>(p, pdl, stream, err)) return true;
+        } else {
+            if (ms >= 6 && v3_try<1, 8, 2, 6, 2>(p, pdl, stream, err)) return true;
+        }
+    }
     if (p.mc <= 8) {
         if (tall && v3_try<1, 16, 1, 4>(p, pdl, stream, err)) return true;
         if (v3_try<1, 8, 2, 5>(p, pdl, stream, err)) return true;
@@ -500,6 +524,13 @@ cudaError_t prepare_w4_v3() {
     e = cudaFuncSetAttribute(k_w4a16_v3<NT, NORM, W, SB, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                              kV3Budget);                                                                        \
     if (e != cudaSuccess) return e;
+#define ZL_SET2(NORM, W, SB, ST)                                                                               \
+    e = cudaFuncSetAttribute(k_w4a16_v3<1, NORM, W, SB, ST, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                             kV3Budget);                                                                        \
+    if (e != cudaSuccess) return e;
+    ZL_SET2(false, 16, 1, 6) ZL_SET2(true, 16, 1, 6) ZL_SET2(false, 16, 1, 5) ZL_SET2(true, 16, 1, 5)
+    ZL_SET2(false, 8, 2, 6) ZL_SET2(true, 8, 2, 6)
+#undef ZL_SET2
     ZL_SET(1, false, 8, 2, 5) ZL_SET(1, true, 8, 2, 5) ZL_SET(1, false, 8, 2, 4) ZL_SET(1, true, 8, 2, 4)
     ZL_SET(1, false, 16, 1, 4) ZL_SET(1, true, 16, 1, 4)
     ZL_SET(2, false, 8, 2, 4) ZL_SET(2, true, 8, 2, 4) ZL_SET(2, false, 16, 1, 4) ZL_SET(2, true, 16, 1, 4)
