@@ -38,6 +38,7 @@ class LlamaDecoder:
             float(l3.get("orig", 8192.0)), quant_type, group_size, int(sym), {"f16": 0, "bf16": 1}[dtype],
             max_batch, max_seq, tp_rank, tp_size, int(use_pdl), int(use_graph), int(tp_int8), int(fuse))
         self.vocab_size = vocab_size
+        self.vocab_shard = vocab_size // tp_size      # lm_head is vocab-parallel: logits come back per rank shard
         self.max_batch = max_batch
         h = ctypes.c_void_p()
         _lib.check(self.lib.zl_llama_create(ctypes.byref(self.cfg), ctypes.byref(h)))
@@ -72,12 +73,13 @@ class LlamaDecoder:
         _lib.check(self.lib.zl_llama_init_synthetic(self.h, seed))
 
     def decode(self, tokens, positions, want_logits=False):
-        """One step: tokens/positions int32 host arrays (B).  Returns next tokens (B) [, logits (B,V) fp32]."""
+        """One step: tokens/positions int32 host arrays (B).  Returns next tokens (B) [, logits (B, V/tp) fp32: this
+        rank's vocabulary shard]."""
         t = np.ascontiguousarray(tokens, dtype=np.int32)
         p = np.ascontiguousarray(positions, dtype=np.int32)
         b = t.size
         nxt = np.empty(b, dtype=np.int32)
-        logits = np.empty((b, self.vocab_size), dtype=np.float32) if want_logits else None
+        logits = np.empty((b, self.vocab_shard), dtype=np.float32) if want_logits else None
         _lib.check(self.lib.zl_llama_decode(
             self.h, t.ctypes.data_as(ctypes.c_void_p), p.ctypes.data_as(ctypes.c_void_p), b,
             nxt.ctypes.data_as(ctypes.c_void_p),
