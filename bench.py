@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tp-int8", action="store_true", help="int8 group-32 payload for the TP all-reduce")
+    ap.add_argument("--requests", type=int, default=32, help="requests for the TTFT/TPOT p50 (0 = skip)")
     ap.add_argument("--fuse", type=int, default=2, help="0: one kernel per reference op; 1: +RMSNorm fused; 2: +qkv RoPE/KV epilogue")
     args = ap.parse_args()
 
@@ -228,7 +229,8 @@ def main():
     max_seq = args.prompt + 2 * W + 2 * args.steps + 16
     dec = LlamaDecoder(quant_type=0 if dense else 5, group_size=128, sym=True, dtype="bf16" if dense else "f16",
                        max_batch=args.batch, max_seq=max_seq, use_pdl=not args.no_pdl, use_graph=not args.no_graph, fuse=args.fuse,
-                       tp_rank=rank, tp_size=world, tp_int8=args.tp_int8, **cfg)
+                       tp_rank=rank, tp_size=world, tp_int8=args.tp_int8,
+                       prefill_chunk=32 if (world == 1 and args.requests > 0) else 0, **cfg)
     comm = None
     if world > 1:
         comm = zdist.TPComm(args.batch * cfg["dim_model"], rank, world)
@@ -332,6 +334,29 @@ def main():
         "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_roof, "peak": peak, "unit": "GB/s",
                           "frac": step_roof / peak},
     }
+    # ---- latency view of the same path: TTFT = chunked prefill of a fresh prompt + first token,
+    # TPOT = (t_total - TTFT) / (n_out - 1), both wall clock through the host API, p50 over --requests requests ----
+    if world == 1 and args.requests > 0:
+        n_out = 16
+        plen = min(args.prompt, max_seq - n_out - 1)
+        ttft, tpot = [], []
+        for r in range(args.requests):
+            ptoks = rng.integers(0, cfg["vocab_size"], size=plen).astype(np.int32)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            t_next = dec.prefill(0, ptoks)
+            t1 = time.perf_counter()
+            tk = np.array([t_next], dtype=np.int32)
+            ps = np.array([plen], dtype=np.int32)
+            for _ in range(n_out - 1):
+                tk = dec.decode(tk, ps)
+                ps = ps + 1
+            t2 = time.perf_counter()
+            ttft.append((t1 - t0) * 1e3)
+            tpot.append((t2 - t1) * 1e3 / (n_out - 1))
+        out["latency"] = {"ttft_ms_p50": float(np.median(ttft)), "tpot_ms_p50": float(np.median(tpot)),
+                          "requests": args.requests, "prompt_tokens": plen, "new_tokens": n_out, "batch": 1,
+                          "prefill": "chunked, 32 tokens per pass"}
     if rank == 0 and not args.no_cpu_baseline:
         v, cores, sample, _ = cpu_reference_path(cfg, not dense, B, budget_s=12.0)
         out["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample}

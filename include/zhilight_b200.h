@@ -293,7 +293,10 @@ typedef struct zl_llama_config {
     int tp_rank, tp_size;
     int use_pdl, use_graph;
     int tp_int8; /* TP all-reduce payload: 0 = activation dtype, 1 = int8 group-32 (REDUCE_TP_INT8 of the reference) */
-    int fuse; /* 0: one kernel per reference operator; 1: RMSNorm folded into the W4 GEMMs; 2: + qkv RoPE/KV-append epilogue */
+    int fuse; /* 0: one kernel per reference operator; 1: RMSNorm folded into the W4 GEMMs; 2: + qkv RoPE/KV-append epilogue;
+               * 3: opt-in persistent whole-model kernel (llama_mega.cu) when the shape fits, else as 2 */
+    int prefill_chunk; /* 0: decode only.  1..32: zl_llama_prefill processes a prompt in chunks of this many tokens
+                        * (chunked prefill, zhilight/config/adapter.py:47-48); W4 models then also keep the ZLW4 layout */
 } zl_llama_config_t;
 
 int zl_llama_create(const zl_llama_config_t* cfg, zl_llama_t** out);
@@ -320,6 +323,11 @@ int zl_llama_step_device(zl_llama_t* m, int B);
 /* read back the device-resident (token, position) state; synchronous. */
 int zl_llama_get_state(zl_llama_t* m, int32_t* tokens_host, int32_t* positions_host, int B);
 int zl_llama_sync(zl_llama_t* m);
+/* Chunked prefill of ONE task (SearchTask prompt, src/generator/batch_generator.cpp:1576): appends tokens_host[0..n) at
+ * positions pos0.. to the task's KV buffers through the same kernels (M = chunk GEMMs, causal len_q = chunk attention)
+ * and returns the greedy next token (and optionally the last position's logits, vocab/tp floats).  Synchronous. */
+int zl_llama_prefill(zl_llama_t* m, int task, const int32_t* tokens_host, int n, int pos0, int32_t* next_token_host,
+                     float* logits_host);
 /* debug: (id, globaltimer ns) records of the persistent decode kernel's last launch (ZL_MEGA_TRACE=1 at finalize);
  * out[0] = record count, then pairs. */
 int zl_llama_mega_trace(zl_llama_t* m, unsigned long long* out, int n_words);

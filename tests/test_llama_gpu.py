@@ -150,3 +150,47 @@ def test_persistent_kernel_is_bit_identical_to_kernel_chain(lib, cuda, cfg, max_
         assert np.isfinite(l2).all()
         np.testing.assert_array_equal(l2, l3)
         np.testing.assert_array_equal(n2, n3)
+
+
+# W4: the M = 32 passes run the fp16-HMMA kernel (fp16 dequant, fp32 accumulate), not the exact-integer M <= 16 kernel
+@pytest.mark.parametrize("quant,dtype,tol", [(5, "f16", 5e-3), (0, "f16", 3e-3), (0, "bf16", 2e-2)])
+def test_chunked_prefill_matches_token_by_token_oracle(lib, cuda, quant, dtype, tol):
+    """zl_llama_prefill (chunks of <= 32 tokens through the M = chunk GEMMs and causal len_q = chunk attention) must
+    leave the same KV state and produce the same next-token logits as feeding the prompt one token at a time."""
+    from zhilight_b200.llama import LlamaDecoder
+    cfg = TINY128 if quant == 5 else TINY
+    sd = omodel.make_state_dict(cfg, quant, 128, False, seed=9, dtype=dtype)
+    dec = LlamaDecoder(quant_type=quant, dtype=dtype, max_batch=2, max_seq=128, prefill_chunk=32, **cfg)
+    dec.load_state_dict(sd)
+    orc = omodel.OracleLlama(cfg, sd, quant, 128, False, dtype, fuse_norm=True)
+    rng = np.random.default_rng(4)
+    prompt = rng.integers(0, cfg["vocab_size"], size=70).astype(np.int32)      # chunks of 32, 32, 6
+    other = rng.integers(0, cfg["vocab_size"], size=5).astype(np.int32)
+    # task 0 gets a short prompt first so that task 1's prefill runs beside existing state
+    n0, l0 = dec.prefill(0, other, want_logits=True)
+    n1, l1 = dec.prefill(1, prompt, want_logits=True)
+    for p, t in enumerate(other):
+        r0 = orc.decode(np.array([t]), [p], tasks=[0])
+    for p, t in enumerate(prompt):
+        r1 = orc.decode(np.array([t]), [p], tasks=[1])
+    assert rel_l2(l0, r0) <= tol and rel_l2(l1, r1) <= tol
+    # continue decoding both tasks from the prefilled KV state
+    tok = np.array([int(np.argmax(r0[0])), int(np.argmax(r1[0]))], dtype=np.int32)
+    pos = np.array([len(other), len(prompt)], dtype=np.int32)
+    for _ in range(3):
+        nxt, logits = dec.decode(tok, pos, want_logits=True)
+        ref = orc.decode(tok, pos, tasks=[0, 1])
+        assert rel_l2(logits, ref) <= tol
+        tok = np.argmax(ref, axis=1).astype(np.int32)
+        pos += 1
+    dec.close()
+
+
+def test_prefill_needs_configuration(lib, cuda):
+    from zhilight_b200 import _lib
+    from zhilight_b200.llama import LlamaDecoder
+    dec = LlamaDecoder(quant_type=0, max_batch=1, max_seq=64, **TINY)
+    dec.init_synthetic(0)
+    with pytest.raises(_lib.ZLError):
+        dec.prefill(0, np.arange(4, dtype=np.int32))
+    dec.close()

@@ -9,8 +9,10 @@
 
 namespace zl {
 
-constexpr int kDenseWarps = 4;
+constexpr int kDenseWarps = 8;
 constexpr int kDenseUnroll = 4;   // k-steps (32 k each) in flight
+// One CTA = kDenseWarps warps = (kDenseWarps / KS) row tiles of 16 weight rows, each split KS ways along K: small N
+// (layer Linears of a 1B model: N/16 = 128 tiles) still puts >= 16 warps of loads in flight on every SM.
 
 template <typename T>
 __device__ __forceinline__ void mma_t(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
@@ -24,30 +26,33 @@ __device__ __forceinline__ void mma_t<__nv_bfloat16>(float (&d)[4], const uint32
     mma_16816_bf16(d, a, b0, b1, d);
 }
 
-template <typename T, typename TO, int NT>
+template <typename T, typename TO, int NT, int KS>
 __global__ void __launch_bounds__(kDenseWarps * 32)
 k_dense_skinny(const T* __restrict__ x, int ldx, const T* __restrict__ w, const T* __restrict__ bias,
                TO* __restrict__ y, int mc, int N, int K) {
+    constexpr int TPC = kDenseWarps / KS;   // tiles per CTA
+    __shared__ float red[KS > 1 ? kDenseWarps : 1][NT][4][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int tile = blockIdx.x * kDenseWarps + warp;
+    const int tile = blockIdx.x * TPC + warp / KS;
+    const int ks = warp % KS;
     const int row0 = tile * 16;
+    const bool live = row0 < N;
     pdl_trigger();
-    if (row0 >= N) {
-        pdl_wait();
-        return;
-    }
     const int ra = min(row0 + g, N - 1), rb = min(row0 + g + 8, N - 1);
     const T* wa = w + (size_t)ra * K + t * 8;
     const T* wb = w + (size_t)rb * K + t * 8;
-    const int steps = K / 32;
+    const int all_steps = K / 32;
+    const int s_lo = (int)((long long)all_steps * ks / KS), steps = (int)((long long)all_steps * (ks + 1) / KS);
 
     uint4 na[kDenseUnroll], nb[kDenseUnroll];
+    if (live) {
 #pragma unroll
-    for (int u = 0; u < kDenseUnroll; ++u) {
-        if (u < steps) {
-            na[u] = ld_nc_na_u4(wa + u * 32);
-            nb[u] = ld_nc_na_u4(wb + u * 32);
+        for (int u = 0; u < kDenseUnroll; ++u) {
+            if (s_lo + u < steps) {
+                na[u] = ld_nc_na_u4(wa + (size_t)(s_lo + u) * 32);
+                nb[u] = ld_nc_na_u4(wb + (size_t)(s_lo + u) * 32);
+            }
         }
     }
     pdl_wait();
@@ -58,7 +63,7 @@ k_dense_skinny(const T* __restrict__ x, int ldx, const T* __restrict__ w, const 
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[nt][c] = 0.f;
 
-    for (int s0 = 0; s0 < steps; s0 += kDenseUnroll) {
+    for (int s0 = s_lo; live && s0 < steps; s0 += kDenseUnroll) {
         uint4 ca[kDenseUnroll], cb[kDenseUnroll];
 #pragma unroll
         for (int u = 0; u < kDenseUnroll; ++u) {
@@ -97,6 +102,24 @@ k_dense_skinny(const T* __restrict__ x, int ldx, const T* __restrict__ w, const 
         }
     }
 
+    if constexpr (KS > 1) {   // split-k partial sums meet in shared memory, added in k order
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) red[warp][nt][c][lane] = acc[nt][c];
+        __syncthreads();
+        if (ks != 0) return;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float sum = acc[nt][c];
+#pragma unroll
+                for (int k2 = 1; k2 < KS; ++k2) sum += red[warp + k2][nt][c][lane];
+                acc[nt][c] = sum;
+            }
+    }
+    if (!live) return;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
@@ -112,14 +135,37 @@ k_dense_skinny(const T* __restrict__ x, int ldx, const T* __restrict__ w, const 
     }
 }
 
+template <typename T, typename TO, int NT>
+static cudaError_t launch_dense_ks(const T* x, int ldx, const T* w, const T* bias, TO* y, int mc, int N, int K,
+                                   bool pdl, cudaStream_t stream) {
+    const int tiles = cdiv(N, 16);
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    const int steps = K / 32;
+    int ks = 1;   // aim for >= 16 warps per SM, keep >= 2 * unroll k-steps per warp
+    while (ks < kDenseWarps && tiles * ks < sms * 16 && steps / (ks * 2) >= 2 * kDenseUnroll) ks *= 2;
+    dim3 block(kDenseWarps * 32);
+#define ZL_DENSE_LAUNCH(KS_)                                                                                      \
+    return launch(k_dense_skinny<T, TO, NT, KS_>, dim3(cdiv(tiles, kDenseWarps / KS_)), block, 0, stream, pdl, x, ldx, \
+                  w, bias, y, mc, N, K)
+    if (ks == 1) ZL_DENSE_LAUNCH(1);
+    if (ks == 2) ZL_DENSE_LAUNCH(2);
+    if (ks == 4) ZL_DENSE_LAUNCH(4);
+    ZL_DENSE_LAUNCH(8);
+#undef ZL_DENSE_LAUNCH
+}
+
 template <typename T, typename TO>
 static cudaError_t launch_dense(const T* x, int ldx, const T* w, const T* bias, TO* y, int mc, int N, int K,
                                 bool pdl, cudaStream_t stream) {
-    const int tiles = cdiv(N, 16);
-    dim3 grid(cdiv(tiles, kDenseWarps)), block(kDenseWarps * 32);
-    if (mc <= 8) return launch(k_dense_skinny<T, TO, 1>, grid, block, 0, stream, pdl, x, ldx, w, bias, y, mc, N, K);
-    if (mc <= 16) return launch(k_dense_skinny<T, TO, 2>, grid, block, 0, stream, pdl, x, ldx, w, bias, y, mc, N, K);
-    return launch(k_dense_skinny<T, TO, 4>, grid, block, 0, stream, pdl, x, ldx, w, bias, y, mc, N, K);
+    if (mc <= 8) return launch_dense_ks<T, TO, 1>(x, ldx, w, bias, y, mc, N, K, pdl, stream);
+    if (mc <= 16) return launch_dense_ks<T, TO, 2>(x, ldx, w, bias, y, mc, N, K, pdl, stream);
+    return launch_dense_ks<T, TO, 4>(x, ldx, w, bias, y, mc, N, K, pdl, stream);
 }
 
 template <typename T>

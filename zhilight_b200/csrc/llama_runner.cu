@@ -83,6 +83,11 @@ struct zl_llama {
     unsigned* d_mega_sync = nullptr;        // [0] barrier counter (zeroed every step), [1] sticky abort flag
     unsigned long long* d_mega_trace = nullptr;
     bool mega_used = false;
+    // chunked prefill (cfg.prefill_chunk > 0): activation buffers hold tok_cap = max(max_batch, chunk) tokens
+    int tok_cap = 0;
+    int32_t* d_tb = nullptr;      // token -> task map of the chunk being prefilled
+    const int32_t* cur_tb = nullptr;   // token -> task map of the launch sequence being enqueued (d_iota at decode)
+    int8_t* d_mask = nullptr;     // (chunk, max_seq) causal mask of the chunk
 };
 
 namespace {
@@ -116,6 +121,24 @@ __global__ void k_advance(int32_t* __restrict__ tokens, int32_t* __restrict__ po
         pos[i] += 1;
     }
 }
+// prefill chunk setup: positions pos0.., token -> task map, the task's buffer length, and the causal mask
+// mask[i][j] = j <= pos0 + i over len_buf = pos0 + n keys (attention_kernel.cu:434-489 mask contract, int8)
+__global__ void k_prefill_setup(int32_t* __restrict__ pos, int32_t* __restrict__ tb, int32_t* __restrict__ lens,
+                                int8_t* __restrict__ mask, int task, int pos0, int n) {
+    const int len_buf = pos0 + n;
+    for (int i = threadIdx.x + blockIdx.x * blockDim.x; i < n * len_buf; i += blockDim.x * gridDim.x) {
+        const int qi = i / len_buf, j = i % len_buf;
+        mask[i] = j <= pos0 + qi ? 1 : 0;
+    }
+    if (blockIdx.x == 0) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            pos[i] = pos0 + i;
+            tb[i] = task;
+        }
+        if (threadIdx.x == 0) lens[task] = len_buf;
+    }
+}
+
 __global__ void k_iota(int32_t* p, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = i;
@@ -218,7 +241,8 @@ int build_w4(zl_llama* m, const std::vector<std::string>& prefixes, const std::v
     ZL_CHECK_SUPPORTED(pbytes > 0);
     // the integer kernel serves every batch size whose staged activations fit shared memory; the fp16-MMA
     // layout is only materialised when the configured max_batch needs it
-    const bool need_half = !zl_w4_int_kernel_fits(m->cfg.max_batch, N, K) || getenv("ZL_W4_FORCE_HALF");
+    const int m_max = m->cfg.prefill_chunk > m->cfg.max_batch ? m->cfg.prefill_chunk : m->cfg.max_batch;
+    const bool need_half = !zl_w4_int_kernel_fits(m_max, N, K) || getenv("ZL_W4_FORCE_HALF");
     RCHECK(dmalloc(&out->packed_i, pbytes));
     RCHECK(zl_w4_pack_v(qw_km, qz_km, sc_km, row_map, out->packed_i, N, K, m->cfg.group_size, m->cfg.sym, 1,
                         m->stream));
@@ -372,30 +396,36 @@ int alloc_runtime(zl_llama* m) {
         k_ptr_table<<<1, 256, 0, m->stream>>>(L.v_addrs, (char*)L.vbuf, kv_task, B);
         ZL_CHECK_LAUNCH();
     }
-    RCHECK(dmalloc(&m->h, (size_t)B * D * 2));
-    RCHECK(dmalloc(&m->xn, (size_t)B * D * 2));
-    RCHECK(dmalloc(&m->pend, (size_t)B * D * 2));
-    RCHECK(dmalloc(&m->qkv, (size_t)B * (m->hq + 2 * m->hkv) * d * 2));
-    RCHECK(dmalloc(&m->q, (size_t)B * m->hq * d * 2));
-    RCHECK(dmalloc(&m->ao, (size_t)B * m->hq * d * 2));
-    RCHECK(dmalloc(&m->gu, (size_t)B * 2 * m->ff * 2));
-    RCHECK(dmalloc(&m->act, (size_t)B * m->ff * 2));
+    const int T = c.prefill_chunk > B ? c.prefill_chunk : B;   // tokens per launch: decode batch or prefill chunk
+    m->tok_cap = T;
+    RCHECK(dmalloc(&m->h, (size_t)T * D * 2));
+    RCHECK(dmalloc(&m->xn, (size_t)T * D * 2));
+    RCHECK(dmalloc(&m->pend, (size_t)T * D * 2));
+    RCHECK(dmalloc(&m->qkv, (size_t)T * (m->hq + 2 * m->hkv) * d * 2));
+    RCHECK(dmalloc(&m->q, (size_t)T * m->hq * d * 2));
+    RCHECK(dmalloc(&m->ao, (size_t)T * m->hq * d * 2));
+    RCHECK(dmalloc(&m->gu, (size_t)T * 2 * m->ff * 2));
+    RCHECK(dmalloc(&m->act, (size_t)T * m->ff * 2));
     RCHECK(dmalloc((void**)&m->logits, (size_t)B * c.vocab_size * 4));
     RCHECK(dmalloc(&m->cand, (size_t)((B * 8 + 15) / 16) * 16));
     RCHECK(dmalloc(&m->cand_all, (size_t)((B * 8 + 15) / 16) * 16 * c.tp_size));
-    RCHECK(dmalloc((void**)&m->cosb, (size_t)B * d * 4));
-    RCHECK(dmalloc((void**)&m->sinb, (size_t)B * d * 4));
-    RCHECK(dmalloc((void**)&m->d_tokens, B * 4));
-    RCHECK(dmalloc((void**)&m->d_pos, B * 4));
+    RCHECK(dmalloc((void**)&m->cosb, (size_t)T * d * 4));
+    RCHECK(dmalloc((void**)&m->sinb, (size_t)T * d * 4));
+    RCHECK(dmalloc((void**)&m->d_tokens, T * 4));
+    RCHECK(dmalloc((void**)&m->d_pos, T * 4));
     RCHECK(dmalloc((void**)&m->d_lens, B * 4));
+    if (c.prefill_chunk > 0) {
+        RCHECK(dmalloc((void**)&m->d_tb, T * 4));
+        RCHECK(dmalloc((void**)&m->d_mask, (size_t)c.prefill_chunk * c.max_seq));
+    }
     RCHECK(dmalloc((void**)&m->d_next, B * 4));
     RCHECK(dmalloc((void**)&m->d_iota, B * 4));
     k_iota<<<1, 256, 0, m->stream>>>(m->d_iota, B);
     ZL_CHECK_LAUNCH();
-    m->attn_ws_bytes = zl_decode_attention_workspace_bytes(B, 1, m->hq, d, c.max_seq);
+    m->attn_ws_bytes = zl_decode_attention_workspace_bytes(T, 1, m->hq, d, c.max_seq);
     RCHECK(dmalloc(&m->attn_ws, m->attn_ws_bytes));
     RCHECK(dmalloc(&m->argmax_ws, zl_argmax_workspace_bytes(B)));
-    ZL_CHECK_CUDA(cudaMallocHost((void**)&m->h_stage, sizeof(int32_t) * (4 * B + 4)));
+    ZL_CHECK_CUDA(cudaMallocHost((void**)&m->h_stage, sizeof(int32_t) * (4 * B + 4 + T)));
     ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
     return ZL_OK;
 }
@@ -477,7 +507,7 @@ int w4_gemm(zl_llama* m, const void* x, int ldx, const W4Lin& w, const void* res
         a.cos = m->cosb;
         a.sin = m->sinb;
         a.q_out = m->q;
-        a.token_batch = m->d_iota;
+        a.token_batch = m->cur_tb;
         a.placement = m->d_pos;
         a.k_addrs = rope_layer->k_addrs;
         a.v_addrs = rope_layer->v_addrs;
@@ -592,8 +622,15 @@ static int debug_skip() {
     return v;
 }
 
-int enqueue_step(zl_llama* m, int B, int len_bucket) {
+// pf != nullptr: one chunk of a prompt (tokens of ONE task at consecutive positions) instead of one token per task
+struct PrefillChunk {
+    int task, pos0, n;
+    bool last;   // run final norm + lm_head + pick on the chunk's last token
+};
+
+int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* pf = nullptr) {
     const auto& c = m->cfg;
+    const int B = pf ? pf->n : n_tasks;   // rows (tokens) of every activation matrix in this launch sequence
     const int skip = debug_skip();
     const int D = c.dim_model, d = c.dim_head, dt = c.dtype, pdl = c.use_pdl;
     cudaStream_t st = m->stream;
@@ -607,13 +644,19 @@ int enqueue_step(zl_llama* m, int B, int len_bucket) {
 
     // grid-barrier counter of the persistent kernel: zeroed first so that the kernel chain below stays kernel->kernel
     if (m->d_mega_sync) ZL_CHECK_CUDA(cudaMemsetAsync(m->d_mega_sync, 0, 4, st));
-    ZL_CHECK_CUDA(launch(k_lens_from_pos, dim3(cdiv(B, 64)), dim3(64), 0, st, false, (const int32_t*)m->d_pos,
-                         m->d_lens, B));
+    if (pf) {
+        k_prefill_setup<<<8, 256, 0, st>>>(m->d_pos, m->d_tb, m->d_lens, m->d_mask, pf->task, pf->pos0, pf->n);
+        ZL_CHECK_LAUNCH();
+    } else {
+        ZL_CHECK_CUDA(launch(k_lens_from_pos, dim3(cdiv(B, 64)), dim3(64), 0, st, false, (const int32_t*)m->d_pos,
+                             m->d_lens, B));
+    }
+    m->cur_tb = pf ? m->d_tb : m->d_iota;
     RCHECK(zl_rope_cos_sin(m->d_pos, m->cosb, m->sinb, B, d, c.rope_theta, c.rope_llama3_factor,
                            c.rope_low_freq_factor, c.rope_high_freq_factor, c.rope_orig_ctx, 1, st));
     RCHECK(zl_embedding(m->d_tokens, m->emb, m->h, B, D, c.vocab_size, dt, 0, st));
     MegaParams mp;
-    const int mega_stages = (w4 && c.fuse >= 3 && !skip) ? mega_plan(m, B, len_bucket, &mp) : 0;
+    const int mega_stages = (w4 && c.fuse >= 3 && !skip && !pf) ? mega_plan(m, B, len_bucket, &mp) : 0;
     m->mega_used = mega_stages != 0;
     if (mega_stages) ZL_CHECK_CUDA(launch_llama_mega(mp, mega_stages, pdl != 0, st));
     for (int l = 0; l < (mega_stages ? 0 : c.num_layers); ++l) {
@@ -641,7 +684,7 @@ int enqueue_step(zl_llama* m, int B, int len_bucket) {
                                         st));
         }
         if (!(w4 && c.fuse >= 2) && !(skip & 64))
-            RCHECK(zl_qkv_rope_append(m->cosb, m->sinb, m->qkv, m->q, m->d_iota, m->d_pos, L.k_addrs, L.v_addrs, B,
+            RCHECK(zl_qkv_rope_append(m->cosb, m->sinb, m->qkv, m->q, m->cur_tb, m->d_pos, L.k_addrs, L.v_addrs, B,
                                       m->hq, m->hkv, d, 1, 1, m->d_lens, dt, pdl, st));
         if (!(skip & 1)) {
             const void* pfp = nullptr;
@@ -649,7 +692,12 @@ int enqueue_step(zl_llama* m, int B, int len_bucket) {
             prefetch_target(m, l, 1, B, &pfp, &pfb);
             zl_decode_attention_set_prefetch(pfp, pfb);
         }
-        if (!(skip & 1))
+        if (pf) {
+            // one task, len_q = chunk, causal int8 mask (Attention::dynamic_batch_forward with len_q > 1, attention.cpp:846-964)
+            RCHECK(zl_decode_attention(m->q, m->d_lens + pf->task, L.k_addrs + pf->task, L.v_addrs + pf->task, m->d_mask,
+                                       scale, pf->pos0 + pf->n, m->ao, 1, pf->n, m->hq, m->hkv, d, 1, m->attn_ws,
+                                       m->attn_ws_bytes, dt, pdl, st));
+        } else if (!(skip & 1))
             RCHECK(zl_decode_attention(m->q, m->d_lens, L.k_addrs, L.v_addrs, nullptr, scale, len_bucket, m->ao, B, 1,
                                        m->hq, m->hkv, d, 1, m->attn_ws, m->attn_ws_bytes, dt, pdl, st));
         if (w4) {
@@ -690,23 +738,34 @@ int enqueue_step(zl_llama* m, int B, int len_bucket) {
             if (tp) RCHECK(zl_allreduce_one_shot(m->comm, m->pend, nullptr, m->pend, (size_t)B * D, dt, c.tp_int8, pdl, st));
         }
     }
-    if (w4) {
+    if (pf) {
+        if (!pf->last) return ZL_OK;
+        // only the last prompt position feeds the head: move it to row 0 semantics by pointing at its row
+        const size_t off = (size_t)(pf->n - 1) * D * 2;
+        if (w4) {
+            RCHECK(zl_rmsnorm((char*)m->h + off, m->ln_f, m->xn, 1, D, c.eps, 1.f, dt, pdl, st));
+        } else {
+            RCHECK(zl_add_rmsnorm((char*)m->h + off, (char*)m->pend + off, m->ln_f, (char*)m->h + off, m->xn, 1, D, c.eps,
+                                  1.f, 0, dt, pdl, st));
+        }
+    } else if (w4) {
         RCHECK(zl_rmsnorm(m->h, m->ln_f, m->xn, B, D, c.eps, 1.f, dt, pdl, st));
     } else {
         RCHECK(zl_add_rmsnorm(m->h, m->pend, m->ln_f, m->h, m->xn, B, D, c.eps, 1.f, 0, dt, pdl, st));
     }
+    const int HB = pf ? 1 : B;   // rows that reach lm_head
     // vocab-parallel lm_head (embedding.cu:353-392): each rank owns vshard rows
     if (!(skip & 32))
-        RCHECK(zl_dense_gemm_skinny(m->xn, D, m->lm_head, nullptr, m->logits, B, m->vshard, D, dt, ZL_F32, pdl, st));
+        RCHECK(zl_dense_gemm_skinny(m->xn, D, m->lm_head, nullptr, m->logits, HB, m->vshard, D, dt, ZL_F32, pdl, st));
     if (!tp) {
-        RCHECK(zl_argmax(m->logits, m->d_next, B, m->vshard, m->argmax_ws, zl_argmax_workspace_bytes(B), pdl, st));
+        RCHECK(zl_argmax(m->logits, m->d_next, HB, m->vshard, m->argmax_ws, zl_argmax_workspace_bytes(HB), pdl, st));
     } else {
         // instead of all-gathering (B, V) logits, exchange one {value, index} candidate per token
-        const int stride = ((B * 8 + 15) / 16) * 2;   // int2 records per rank slot (16-byte multiple)
-        RCHECK(zl_argmax_candidates(m->logits, m->cand, B, m->vshard, c.tp_rank * m->vshard, m->argmax_ws,
-                                    zl_argmax_workspace_bytes(B), pdl, st));
+        const int stride = ((HB * 8 + 15) / 16) * 2;   // int2 records per rank slot (16-byte multiple)
+        RCHECK(zl_argmax_candidates(m->logits, m->cand, HB, m->vshard, c.tp_rank * m->vshard, m->argmax_ws,
+                                    zl_argmax_workspace_bytes(HB), pdl, st));
         RCHECK(zl_allgather_small(m->comm, m->cand, m->cand_all, (size_t)stride * 8, pdl, st));
-        RCHECK(zl_argmax_merge(m->cand_all, m->d_next, B, c.tp_size, stride, pdl, st));
+        RCHECK(zl_argmax_merge(m->cand_all, m->d_next, HB, c.tp_size, stride, pdl, st));
     }
     return ZL_OK;
 }
@@ -760,6 +819,7 @@ extern "C" int zl_llama_create(const zl_llama_config_t* cfg, zl_llama_t** out) {
                        cfg->dim_ff % cfg->tp_size == 0 && cfg->vocab_size % cfg->tp_size == 0);
     ZL_CHECK_SUPPORTED(cfg->quant_type == 0 || cfg->group_size == zl::kW4GroupK);
     ZL_CHECK_ARG(cfg->fuse >= 0 && cfg->fuse <= 3);
+    ZL_CHECK_ARG(cfg->prefill_chunk >= 0 && cfg->prefill_chunk <= 32);
     ZL_CHECK_SUPPORTED(cfg->fuse < 2 || cfg->dim_head % 32 == 0);
     RCHECK(zl_prepare());
     zl_llama* m = new zl_llama();
@@ -799,7 +859,7 @@ extern "C" void zl_llama_destroy(zl_llama_t* m) {
     for (void* p : {m->emb, m->lm_head_tied ? nullptr : m->lm_head, m->ln_f, m->h, m->xn, m->qkv, m->q, m->ao, m->act,
                     m->pend, m->gu, (void*)m->logits, (void*)m->cosb, (void*)m->sinb, (void*)m->d_tokens,
                     (void*)m->d_pos, (void*)m->d_lens, (void*)m->d_next, (void*)m->d_iota, m->attn_ws, m->argmax_ws, (void*)m->d_mega_layers, (void*)m->d_mega_sync,
-                    (void*)m->d_mega_trace})
+                    (void*)m->d_mega_trace, (void*)m->d_tb, (void*)m->d_mask})
         if (p) cudaFree(p);
     if (m->h_stage) cudaFreeHost(m->h_stage);
     cudaStreamDestroy(m->stream);
@@ -1036,6 +1096,40 @@ extern "C" int zl_llama_sync(zl_llama_t* m) {
             return ZL_ERR_STATE;
         }
     }
+    return ZL_OK;
+}
+
+extern "C" int zl_llama_prefill(zl_llama_t* m, int task, const int32_t* tokens_host, int n, int pos0,
+                                int32_t* next_token_host, float* logits_host) {
+    ZL_CHECK_ARG(m && m->finalized && tokens_host && next_token_host && n > 0 && pos0 >= 0);
+    ZL_CHECK_ARG(task >= 0 && task < m->cfg.max_batch);
+    const int chunk = m->cfg.prefill_chunk;
+    if (chunk <= 0) {
+        zl_set_last_error(__FILE__, __LINE__, "zl_llama_prefill needs cfg.prefill_chunk > 0");
+        return ZL_ERR_STATE;
+    }
+    if (pos0 + n > m->cfg.max_seq) {
+        zl_set_last_error(__FILE__, __LINE__, "prompt does not fit the KV buffers (max_seq)");
+        return ZL_ERR_STATE;
+    }
+    int32_t* h_tok = m->h_stage + 4 * m->cfg.max_batch + 4;   // pinned staging for one chunk of token ids
+    for (int c0 = 0; c0 < n; c0 += chunk) {
+        const int cn = (n - c0) < chunk ? (n - c0) : chunk;
+        if (c0 > 0) ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));   // staging buffer reuse
+        for (int i = 0; i < cn; ++i) {
+            ZL_CHECK_ARG(tokens_host[c0 + i] >= 0 && tokens_host[c0 + i] < m->cfg.vocab_size);
+            h_tok[i] = tokens_host[c0 + i];
+        }
+        ZL_CHECK_CUDA(cudaMemcpyAsync(m->d_tokens, h_tok, cn * 4, cudaMemcpyHostToDevice, m->stream));
+        PrefillChunk pc{task, pos0 + c0, cn, c0 + cn == n};
+        RCHECK(enqueue_step(m, 1, 0, &pc));
+    }
+    ZL_CHECK_CUDA(cudaMemcpyAsync(m->h_stage + 3 * m->cfg.max_batch, m->d_next, 4, cudaMemcpyDeviceToHost, m->stream));
+    if (logits_host)
+        ZL_CHECK_CUDA(cudaMemcpyAsync(logits_host, m->logits, (size_t)m->vshard * 4, cudaMemcpyDeviceToHost, m->stream));
+    ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+    *next_token_host = m->h_stage[3 * m->cfg.max_batch];
+    if (pos0 + n > m->cur_max_len) m->cur_max_len = pos0 + n;
     return ZL_OK;
 }
 

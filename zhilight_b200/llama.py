@@ -29,14 +29,15 @@ QUANT_NONE, QUANT_GPTQ, QUANT_AWQ = 0, 5, 6     # model_config.hpp:132-144
 class LlamaDecoder:
     def __init__(self, num_layers, dim_model, num_heads, num_kv_heads, dim_head, dim_ff, vocab_size, eps=1e-5,
                  rope_theta=10000.0, rope_llama3=None, quant_type=QUANT_NONE, group_size=128, sym=False,
-                 dtype="f16", max_batch=1, max_seq=512, use_pdl=True, use_graph=True, tp_rank=0, tp_size=1, fuse=2, tp_int8=False):
+                 dtype="f16", max_batch=1, max_seq=512, use_pdl=True, use_graph=True, tp_rank=0, tp_size=1, fuse=2, tp_int8=False,
+                 prefill_chunk=0):
         self.lib = _lib.load()
         l3 = rope_llama3 or {}
         self.cfg = _lib.LlamaConfig(
             num_layers, dim_model, num_heads, num_kv_heads, dim_head, dim_ff, vocab_size, eps, rope_theta,
             float(l3.get("factor", 0.0)), float(l3.get("low", 1.0)), float(l3.get("high", 4.0)),
             float(l3.get("orig", 8192.0)), quant_type, group_size, int(sym), {"f16": 0, "bf16": 1}[dtype],
-            max_batch, max_seq, tp_rank, tp_size, int(use_pdl), int(use_graph), int(tp_int8), int(fuse))
+            max_batch, max_seq, tp_rank, tp_size, int(use_pdl), int(use_graph), int(tp_int8), int(fuse), int(prefill_chunk))
         self.vocab_size = vocab_size
         self.vocab_shard = vocab_size // tp_size      # lm_head is vocab-parallel: logits come back per rank shard
         self.max_batch = max_batch
@@ -85,6 +86,16 @@ class LlamaDecoder:
             nxt.ctypes.data_as(ctypes.c_void_p),
             logits.ctypes.data_as(ctypes.c_void_p) if want_logits else None))
         return (nxt, logits) if want_logits else nxt
+
+    def prefill(self, task, tokens, pos0=0, want_logits=False):
+        """Chunked prefill of one task's prompt; returns the greedy next token [, logits of the last position]."""
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        nxt = np.empty(1, dtype=np.int32)
+        logits = np.empty((1, self.vocab_shard), dtype=np.float32) if want_logits else None
+        _lib.check(self.lib.zl_llama_prefill(
+            self.h, int(task), t.ctypes.data_as(ctypes.c_void_p), t.size, int(pos0),
+            nxt.ctypes.data_as(ctypes.c_void_p), logits.ctypes.data_as(ctypes.c_void_p) if want_logits else None))
+        return (int(nxt[0]), logits) if want_logits else int(nxt[0])
 
     def set_state(self, tokens, positions):
         t = np.ascontiguousarray(tokens, dtype=np.int32)
