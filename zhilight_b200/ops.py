@@ -285,8 +285,9 @@ def element_add_scale(a, b, scale=1.0):
 def gate_mul(gate, up, act="silu"):
     t, f = gate.shape
     out = torch.empty((t, f), dtype=gate.dtype, device=gate.device)
-    _lib.call("zl_gate_mul", ctypes.c_void_p(gate.data_ptr()), gate.stride(0), _p(up),
-              up.stride(0) if up is not None else 0, _p(out), f, t, f, 0 if act == "silu" else 1, _dt(gate), _stream())
+    # strided views are fine here: the C entry point takes row strides
+    _lib.call("zl_gate_mul", ctypes.c_void_p(gate.data_ptr()), gate.stride(0),
+              ctypes.c_void_p(up.data_ptr()) if up is not None else None, up.stride(0) if up is not None else 0, _p(out), f, t, f, 0 if act == "silu" else 1, _dt(gate), _stream())
     return out
 
 
