@@ -152,6 +152,9 @@ int zl_fp8_quant_per_tensor(const void* x, void* q, float* scale, size_t n, int 
  * kernel: y(M,N) = T(acc * x_scale * w_scale) (+bias).  xq (M,K) int8/e4m3; w (N,K) int8/e4m3 row-major (the
  * reference's parameter layout); kind ZL_W8_INT8: x_scale (M) f32, w_scale (N) of w_scale_dtype (ZL_F32 or dtype);
  * kind ZL_W8_FP8: both scales one f32.  INT8 results are bit-identical to the reference's three-kernel path. */
+/* int8_op::quant_scale_back (quant_kernel.cu:231-306) stand-alone: y = T(float(acc) * x_scale[m] * w_scale[n]). */
+int zl_int8_scale_back(const int32_t* acc, const float* x_scale, const void* w_scale, int w_scale_dtype, void* y, int M,
+                       int N, int dtype, zl_stream_t stream);
 int zl_w8a8_gemm(const void* xq, const float* x_scale, const void* w, const void* w_scale, int w_scale_dtype,
                  const void* bias, void* y, int M, int N, int K, int kind, int dtype, int pdl, zl_stream_t stream);
 

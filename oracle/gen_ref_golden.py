@@ -23,8 +23,8 @@ LIB = os.path.join(HERE, "_ref", "libzl_ref.so")
 class Ref:
     """ctypes front end of oracle/ref_shim.cu (device pointers in, device pointers out)."""
 
-    def __init__(self, mem_bytes=2 << 30):
-        self.lib = ctypes.CDLL(LIB)
+    def __init__(self, mem_bytes=2 << 30, lib_path=None):
+        self.lib = ctypes.CDLL(lib_path or LIB)
         self.lib.zlref_last_error.restype = ctypes.c_char_p
         self.dev = torch.device("cuda:0")
         self._chk(self.lib.zlref_init(0, ctypes.c_size_t(mem_bytes)))
@@ -231,9 +231,9 @@ def allreduce_int8_with_reference_kernels(ref, parts):
     return out.cpu().numpy().reshape(parts[0].shape)
 
 
-def main(out_dir):
+def main(out_dir, lib_path=None):
     os.makedirs(out_dir, exist_ok=True)
-    ref = Ref()
+    ref = Ref(lib_path=lib_path)
     n = lambda t: t.cpu().numpy()
 
     c = gc.case_gptq_layout()
@@ -310,6 +310,9 @@ def main(out_dir):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "..", "gpurun_out", "golden"))
+    # usage: gen_ref_golden.py [out_dir] [shim library]   (default: the reference's own kernels, oracle/_ref/libzl_ref.so;
+    # oracle/_ref/libzl_dropin.so runs the same calls through integration/zl_nn_dropin.cpp -> libzhilight_b200.so)
+    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "..", "gpurun_out", "golden"),
+         sys.argv[2] if len(sys.argv) > 2 else None)
     sys.stdout.flush()
     os._exit(0)      # bmengine statics are torn down after the CUDA driver at interpreter exit

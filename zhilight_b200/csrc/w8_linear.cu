@@ -175,6 +175,16 @@ k_fp8_quant_per_tensor(const T* __restrict__ x, uint8_t* __restrict__ q, float* 
     }
 }
 
+// quant_scale_back (quant_kernel.cu:231-246) for callers that still hold an int32 accumulator
+template <typename T>
+__global__ void k_int8_scale_back(const int32_t* __restrict__ acc, const float* __restrict__ sx, const void* __restrict__ sw,
+                                  int sw_f32, T* __restrict__ y, int N) {
+    const int r = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    const float s_w = sw_f32 ? static_cast<const float*>(sw)[c] : to_f32<T>(static_cast<const T*>(sw)[c]);
+    y[(size_t)r * N + c] = from_f32<T>(__fmul_rn(__fmul_rn((float)acc[(size_t)r * N + c], sx[r]), s_w));
+}
+
 // ---------------------------------------------------------------------------------------------
 // GEMM: y(M,N) = scale-back( xq(M,K) . wq(N,K)^T )
 // ---------------------------------------------------------------------------------------------
@@ -389,6 +399,22 @@ extern "C" int zl_fp8_quant_per_tensor(const void* x, void* q, float* scale, siz
         e = launch(k_fp8_quant_per_tensor<__nv_bfloat16>, dim3(ctas), dim3(256), 0, stream, pdl != 0,
                    static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(q), scale, n);
     ZL_CHECK_CUDA(e);
+    return ZL_OK;
+}
+
+extern "C" int zl_int8_scale_back(const int32_t* acc, const float* x_scale, const void* w_scale, int w_scale_dtype,
+                                  void* y, int M, int N, int dtype, zl_stream_t stream) {
+    ZL_CHECK_ARG(acc && x_scale && w_scale && y && M > 0 && N > 0);
+    ZL_CHECK_ARG(dtype == ZL_F16 || dtype == ZL_BF16);
+    ZL_CHECK_ARG(w_scale_dtype == ZL_F32 || w_scale_dtype == dtype);
+    dim3 grid(cdiv(N, 256), M);
+    if (dtype == ZL_F16)
+        k_int8_scale_back<__half><<<grid, 256, 0, stream>>>(acc, x_scale, w_scale, w_scale_dtype == ZL_F32,
+                                                            static_cast<__half*>(y), N);
+    else
+        k_int8_scale_back<__nv_bfloat16><<<grid, 256, 0, stream>>>(acc, x_scale, w_scale, w_scale_dtype == ZL_F32,
+                                                                   static_cast<__nv_bfloat16*>(y), N);
+    ZL_CHECK_LAUNCH();
     return ZL_OK;
 }
 
