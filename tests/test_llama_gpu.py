@@ -126,10 +126,12 @@ LAYER8B = dict(num_layers=3, dim_model=4096, num_heads=32, num_kv_heads=8, dim_h
 
 
 @pytest.mark.parametrize("cfg,max_batch", [(TINY, 3), (TINY128, 3), (LAYER8B, 2)], ids=["d64", "d128", "llama8b-layers"])
-def test_persistent_kernel_is_bit_identical_to_kernel_chain(lib, cuda, cfg, max_batch):
-    """fuse=3 (one persistent kernel for all layers, grid barriers between phases) performs the same arithmetic in the
-    same order as fuse=2 (kernel per op): logits must be EQUAL, on the toy shapes and on Llama-3.1-8B's real layer
-    shapes (wide qkv / gate_up, tall o / down, all 148 CTAs busy), for changing batch sizes and positions."""
+def test_persistent_kernel_matches_kernel_chain(lib, cuda, cfg, max_batch):
+    """fuse=3 (one persistent kernel for all layers, grid barriers between phases) against fuse=2 (kernel per op) on the
+    toy shapes and on Llama-3.1-8B's real layer shapes (wide qkv / gate_up, tall o / down, all 148 CTAs busy), for
+    changing batch sizes and positions.  Both are exact-integer GEMMs; since the kernel chain packs the two activation
+    digits into one IMMA (15-bit mantissas) and the persistent kernel keeps 16-bit mantissas in two IMMAs, they agree to
+    fp16 rounding, not bit for bit (ZL_W4_NO_ONE=1 restores bit equality)."""
     from zhilight_b200.llama import LlamaDecoder
     outs = []
     for fuse in (2, 3):
@@ -148,8 +150,7 @@ def test_persistent_kernel_is_bit_identical_to_kernel_chain(lib, cuda, cfg, max_
         outs.append(res)
     for (n2, l2), (n3, l3) in zip(*outs):
         assert np.isfinite(l2).all()
-        np.testing.assert_array_equal(l2, l3)
-        np.testing.assert_array_equal(n2, n3)
+        assert rel_l2(l3, l2) <= 1e-3
 
 
 # W4: the M = 32 passes run the fp16-HMMA kernel (fp16 dequant, fp32 accumulate), not the exact-integer M <= 16 kernel

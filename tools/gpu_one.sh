@@ -1,0 +1,15 @@
+#!/bin/bash
+timeout 600 python -m pytest tests/test_w4a16_int_gpu.py tests/test_llama_gpu.py -m gpu -q -x --timeout 120 --timeout-method thread -p no:cacheprovider 2>&1 | tail -3
+run() { timeout 300 python bench.py --steps 64 --warmup 4 --no-cpu-baseline --requests 0 $2 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    try: d=json.loads(l)
+    except Exception: print(l.strip()[:300]); continue
+    print('$1', round(d['value'],1), 'tok/s', round(d['ms_per_step'],4), 'ms', 'e2e', round(d['e2e']['value'],1), 'gemm us/launch', round(d['roofline']['us_per_launch'],2), 'frac', round(d['roofline']['frac'],3))
+"; }
+run "one (new default)" ""
+ZL_W4_NO_ONE=1 run "no-one (old)" ""
+echo "== lnw probe (ln_w not loaded; results invalid)"
+ZL_W4_DEBUG=26 LAYERS=4 timeout 200 python tools/trace_step.py 2>&1 | tail -4
+echo "== normal"
+ZL_W4_DEBUG=10 LAYERS=4 timeout 200 python tools/trace_step.py 2>&1 | tail -4

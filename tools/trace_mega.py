@@ -44,7 +44,12 @@ per = {}
 for i, (idn, ts) in enumerate(rec):
     dt = (ts - prev) / 1e3
     key = int(idn) % 1000
-    if i < 30:
+    if int(idn) >= 10000:
+        ph, sub = int(idn) // 10000 - 1, int(idn) % 1000
+        print("L%-2d   phase %d %-10s t=%9.2f us  (+%6.2f)" % ((int(idn) % 10000) // 1000, ph, "staged" if sub == 100 else "tile %d k-loop done" % (sub - 200), (ts - t0) / 1e3, dt))
+        prev = ts
+        continue
+    if i < 60:
         print("L%-2d %-16s t=%9.2f us  (+%6.2f)" % (int(idn) // 1000, NAMES.get(key, str(key)), (ts - t0) / 1e3, dt))
     per.setdefault(key, []).append(dt)
     prev = ts

@@ -9,7 +9,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ["ZL_W4_DEBUG"] = "2"
+os.environ["ZL_W4_DEBUG"] = os.environ.get("ZL_W4_DEBUG", "2")   # 10 = 2 | 8: extra stamps inside staging
 from zhilight_b200 import _lib  # noqa: E402
 from zhilight_b200.llama import LlamaDecoder, MODEL_PRESETS  # noqa: E402
 
@@ -53,6 +53,9 @@ for i, r in enumerate(rec[: 4 * min(layers, 4)]):
     end = v[-1]
     print("%-8s entry %7.2f  ring %6.2f  wait_done %7.2f  staged %7.2f  end %7.2f | span %5.2f  since_prev_end %6.2f  staging %5.2f" % (
         names[i % 4], v[0], v[1] - v[0], v[2], v[3], end, end - v[2], v[2] - prev_end, v[3] - v[2]))
+    if int(os.environ["ZL_W4_DEBUG"]) & 8:
+        # stamps: entry, ring, wait_done, warp0 staged, all staged, rstd ready (= "staged"), tiles..., end
+        print("         raw deltas since wait_done: " + " ".join("%.2f" % (x - v[2]) for x in v[3:]))
     prev_end = end
 per = {k: [] for k in names}
 gaps = {k: [] for k in names}

@@ -199,7 +199,17 @@ struct MegaGemmArgs {
     __half* y;            // RESIDUAL: h (in/out); SWIGLU: act
     const MegaLayer* L;   // QKV: KV pointer tables
     int epi;
+    unsigned long long* tr;   // debug timeline of CTA 0 (null: off)
+    int* tr_n;
+    int tr_id;
 };
+__device__ __forceinline__ void mega_stamp(const MegaGemmArgs& a, int sub_id) {
+    if (a.tr && *a.tr_n < 255) {
+        a.tr[1 + 2 * *a.tr_n] = (unsigned long long)(a.tr_id + sub_id);
+        a.tr[2 + 2 * *a.tr_n] = globaltimer_ns();
+        a.tr[0] = ++*a.tr_n;
+    }
+}
 
 // One GEMM phase for this CTA: stage x (whole K) as block-floating-point ints, then walk this warp's tiles.
 // NORM / EPI are runtime (CTA-uniform) so that the kernel holds ONE copy of this code, called from one site.
@@ -294,6 +304,7 @@ __device__ __forceinline__ void mega_gemm_phase(const MegaParams& p, const MegaG
         __syncthreads();
     }
 
+    mega_stamp(a, 100);   // staged
     // ---- tiles ----
     for (int ti = 0; ti < m.my_tiles; ++ti) {
         const int st = m.tile0 + ti * m.tile_stride;
@@ -375,6 +386,7 @@ __device__ __forceinline__ void mega_gemm_phase(const MegaParams& p, const MegaG
             if (lane == 0 && prod.remaining > 0) prod.issue(p, warp, ring, bars, pol);   // refills the slot just drained
         }
 
+        mega_stamp(a, 200 + ti);   // this warp's blocks of tile ti consumed
         // ---- split-k reduction across the warps of this sub-CTA + epilogue ----
         float* rbuf = red + (ti & 1) * (WARPS * 256);
         float* myred = rbuf + wl * 256;
@@ -577,6 +589,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) k_llama_mega(const MegaParams
             } else {                // h += act . Wdown
                 a.x = p.act; a.ldx = a.K; a.ln_w = nullptr; a.y = p.h; a.epi = kMegaEpiResidual;
             }
+            a.tr = (l < 2) ? tr : nullptr;
+            a.tr_n = &tr_n;
+            a.tr_id = 1000 * l + 10000 * (ph + 1);
             mega_gemm_phase<STAGES>(p, a, smem, prod, pol, c_slot, c_parity);
             stamp(1000 * l + 10 + ph);
             if (!mega_grid_sync(p.sync, target, s_flag)) return;

@@ -66,7 +66,11 @@ __device__ __forceinline__ void sub_barrier(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int NT, bool NORM, int WARPS, int SUBS, int STAGES, int RT = NT * 8>
+// PACK (mc <= 4): the MMA N dimension (8 columns) is mostly padding at tiny batch, so the two 8-bit digits of the
+// 16-bit activation mantissas share ONE IMMA: column 2i carries token i's high digit, column 2i+1 its low digit, both
+// signed (m = 256*hi' + lo', lo' = int8(m & 0xff), hi' = (m + 128) >> 8, |m| <= 2^14).  Half the IMMAs, half the B
+// loads, and the per-group int->float epilogue only touches real tokens.
+template <int NT, bool NORM, int WARPS, int SUBS, int STAGES, int RT = NT * 8, bool PACK = false>
 __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Params p) {
     using S = V3Smem<NT, WARPS, SUBS, STAGES, RT>;
     constexpr int WT = WARPS * SUBS;
@@ -148,7 +152,9 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
 #pragma unroll
         for (int gl = 0; gl < kMaxNg; ++gl) {
             const int gi = warp + gl * WT;
-            if (gi < G) lnw[gl] = *reinterpret_cast<const uint2*>(p.ln_w + gi * kW4GroupK + lane * 4);
+            if (gi < G)
+                lnw[gl] = (p.dbg & 16) ? make_uint2(0x3c003c00u, 0x3c003c00u)   // timing probe: 1.0h (results are wrong)
+                                       : *reinterpret_cast<const uint2*>(p.ln_w + gi * kW4GroupK + lane * 4);
         }
     }
     __syncwarp();
@@ -186,15 +192,19 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
                 // 2^e with m = x * 2^-e in (-2^15, 2^15): e = floor(log2 amax) - 14
                 const uint32_t ex = (amax_bits >> 23) & 0xffu;
                 const bool zero = ex < 20u || ex == 0xffu;   // all-zero / tiny / non-finite group -> contributes 0
-                const float sg = zero ? 1.0f : __uint_as_float((ex - 14u) << 23);
-                const float inv = zero ? 0.0f : __uint_as_float((268u - ex) << 23);
+                // PACK keeps one bit of headroom (|m| <= 2^14) so that the rounded-up high digit still fits int8
+                constexpr uint32_t kE = PACK ? 13u : 14u;
+                const float sg = zero ? 1.0f : __uint_as_float((ex - kE) << 23);
+                const float inv = zero ? 0.0f : __uint_as_float((254u + kE - ex) << 23);
                 const int m0 = __float2int_rn(a.x * inv), m1 = __float2int_rn(a.y * inv);
                 const int m2 = __float2int_rn(b.x * inv), m3 = __float2int_rn(b.y * inv);
-                // byte 0 of each m -> lo, byte 1 -> hi (two's complement high byte == floor(m / 256)): 6 PRMTs
+                // byte 0 of each m -> lo, byte 1 -> hi (two's complement high byte == floor(m / 256)): 6 PRMTs.
+                // PACK: lo is read as SIGNED, so hi = floor((m + 128) / 256) = byte 1 of m + 128.
+                constexpr int kR = PACK ? 128 : 0;
                 const uint32_t lo = __byte_perm(__byte_perm((uint32_t)m0, (uint32_t)m1, 0x0040),
                                                 __byte_perm((uint32_t)m2, (uint32_t)m3, 0x0040), 0x5410);
-                const uint32_t hi = __byte_perm(__byte_perm((uint32_t)m0, (uint32_t)m1, 0x0051),
-                                                __byte_perm((uint32_t)m2, (uint32_t)m3, 0x0051), 0x5410);
+                const uint32_t hi = __byte_perm(__byte_perm((uint32_t)(m0 + kR), (uint32_t)(m1 + kR), 0x0051),
+                                                __byte_perm((uint32_t)(m2 + kR), (uint32_t)(m3 + kR), 0x0051), 0x5410);
                 *reinterpret_cast<uint32_t*>(xs_hi + tok * row_b + gi * 128 + lane * 4) = hi;
                 *reinterpret_cast<uint32_t*>(xs_lo + tok * row_b + gi * 128 + lane * 4) = lo;
                 const int sm = __reduce_add_sync(0xffffffffu, m0 + m1 + m2 + m3);
@@ -206,7 +216,9 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
             if (lane == 0) s_ss[warp * (NT * 8) + tok] = sq;
         }
     }
+    if (p.dbg & 8) stamp();   // warp 0 finished its groups (loads landed + quantised)
     __syncthreads();
+    if (p.dbg & 8) stamp();   // all warps staged
     if (NORM) {
         if (threadIdx.x < p.mc) {
             float v = 0.f;
@@ -238,42 +250,28 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
                 c_parity ^= 1u;
             }
             const int gi = g_begin + i;
-            // B fragments: 32 contiguous bytes of each piece per lane
-            uint4 bh[NT][2], bl[NT][2];
-            int2 tab[NT][2];
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-                const int tok = nt * 8 + g;
-                if (tok < p.mc) {
-                    const uint8_t* ph = xs_hi + tok * row_b + gi * 128 + t * 32;
-                    const uint8_t* pl = xs_lo + tok * row_b + gi * 128 + t * 32;
-                    bh[nt][0] = *reinterpret_cast<const uint4*>(ph);
-                    bh[nt][1] = *reinterpret_cast<const uint4*>(ph + 16);
-                    bl[nt][0] = *reinterpret_cast<const uint4*>(pl);
-                    bl[nt][1] = *reinterpret_cast<const uint4*>(pl + 16);
-                } else {
-                    bh[nt][0] = bh[nt][1] = bl[nt][0] = bl[nt][1] = make_uint4(0, 0, 0, 0);
+            if constexpr (PACK) {
+                // B fragment column n = g carries token g>>1, digit g&1 (0: high, 1: low); 32 contiguous bytes per lane
+                uint4 bv[2];
+                {
+                    const int tok = g >> 1;
+                    if (tok < p.mc) {
+                        const uint8_t* pp = ((g & 1) ? xs_lo : xs_hi) + tok * row_b + gi * 128 + t * 32;
+                        bv[0] = *reinterpret_cast<const uint4*>(pp);
+                        bv[1] = *reinterpret_cast<const uint4*>(pp + 16);
+                    } else {
+                        bv[0] = bv[1] = make_uint4(0, 0, 0, 0);
+                    }
                 }
-                // group table of the two tokens this lane's accumulators belong to (C columns 2t, 2t+1)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int tc = nt * 8 + 2 * t + e;
-                    tab[nt][e] = tc < p.mc ? xs_tab[gi * p.mc + tc] : make_int2(0, 0);
-                }
-            }
-
-            mbar_wait(&bars[s], parity);
-            const uint8_t* blk = ring + s * kW4BlockBytes;
-            if (p.dbg & 1) {
-                acc[0][0][0] += __uint_as_float(*reinterpret_cast<const uint32_t*>(blk + lane * 4)) * 1e-30f;
-            } else {
-                int ah[2][NT][4], al[2][NT][4];
+                // C columns (2t, 2t+1) = (high, low) digit sums of token t: this lane finishes token t
+                const int2 tb = t < p.mc ? xs_tab[gi * p.mc + t] : make_int2(0, 0);
+                mbar_wait(&bars[s], parity);
+                const uint8_t* blk = ring + s * kW4BlockBytes;
+                int cc[2][4];
 #pragma unroll
                 for (int tt = 0; tt < 2; ++tt)
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) ah[tt][nt][c] = al[tt][nt][c] = 0;
+                    for (int c = 0; c < 4; ++c) cc[tt][c] = 0;
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     uint4 wv[2];
@@ -284,36 +282,106 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
                     for (int jp = 0; jp < 2; ++jp) {
                         const int j = hh * 2 + jp;   // k-step 0..3
 #pragma unroll
-                        for (int tt = 0; tt < 2; ++tt) {   // the two 16-row tiles interleave: independent chains
+                        for (int tt = 0; tt < 2; ++tt) {
                             const uint32_t w0 = jp ? wv[tt].z : wv[tt].x;
                             const uint32_t w1 = jp ? wv[tt].w : wv[tt].y;
                             const uint32_t a[4] = {w0 & 0x0f0f0f0fu, w0 & 0xf0f0f0f0u, w1 & 0x0f0f0f0fu,
                                                    w1 & 0xf0f0f0f0u};
-#pragma unroll
-                            for (int nt = 0; nt < NT; ++nt) {
-                                const uint4 vh = bh[nt][j >> 1], vl = bl[nt][j >> 1];
-                                imma_u8s8(ah[tt][nt], a, (j & 1) ? vh.z : vh.x, (j & 1) ? vh.w : vh.y);
-                                imma_u8u8(al[tt][nt], a, (j & 1) ? vl.z : vl.x, (j & 1) ? vl.w : vl.y);
-                            }
+                            const uint4 v = bv[j >> 1];
+                            imma_u8s8(cc[tt], a, (j & 1) ? v.z : v.x, (j & 1) ? v.w : v.y);
                         }
                     }
                 }
-                // exact integer group result, then one fp32 multiply-add per element
+                const float sgf = __int_as_float(tb.y);
 #pragma unroll
                 for (int tt = 0; tt < 2; ++tt) {
                     const __half2 sc = *reinterpret_cast<const __half2*>(blk + kW4ScaleOff + (tt * 8 + g) * 4);
                     const int zz = blk[kW4ZeroOff + tt * 8 + g];
                     const int z_lo = zz & 0xF, z_hi16 = zz & 0xF0;          // zero of row g ; 16 * zero of row g+8
                     const float s_lo = __low2float(sc), s_hi = __high2float(sc) * 0.0625f;
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const int2 tb = tab[nt][c & 1];
-                            const int zc = (c >> 1) ? z_hi16 : z_lo;
-                            const int r = ah[tt][nt][c] * 256 + al[tt][nt][c] - zc * tb.x;
-                            const float f = ((c >> 1) ? s_hi : s_lo) * __int_as_float(tb.y);
-                            acc[tt][nt][c] = fmaf((float)r, f, acc[tt][nt][c]);
+                    const int r0 = cc[tt][0] * 256 + cc[tt][1] - z_lo * tb.x;      // row g
+                    const int r1 = cc[tt][2] * 256 + cc[tt][3] - z_hi16 * tb.x;    // row g + 8 (x16 folded in s_hi)
+                    acc[tt][0][0] = fmaf((float)r0, s_lo * sgf, acc[tt][0][0]);
+                    acc[tt][0][2] = fmaf((float)r1, s_hi * sgf, acc[tt][0][2]);
+                }
+            } else {
+                // B fragments: 32 contiguous bytes of each piece per lane
+                uint4 bh[NT][2], bl[NT][2];
+                int2 tab[NT][2];
+    #pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const int tok = nt * 8 + g;
+                    if (tok < p.mc) {
+                        const uint8_t* ph = xs_hi + tok * row_b + gi * 128 + t * 32;
+                        const uint8_t* pl = xs_lo + tok * row_b + gi * 128 + t * 32;
+                        bh[nt][0] = *reinterpret_cast<const uint4*>(ph);
+                        bh[nt][1] = *reinterpret_cast<const uint4*>(ph + 16);
+                        bl[nt][0] = *reinterpret_cast<const uint4*>(pl);
+                        bl[nt][1] = *reinterpret_cast<const uint4*>(pl + 16);
+                    } else {
+                        bh[nt][0] = bh[nt][1] = bl[nt][0] = bl[nt][1] = make_uint4(0, 0, 0, 0);
+                    }
+                    // group table of the two tokens this lane's accumulators belong to (C columns 2t, 2t+1)
+    #pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int tc = nt * 8 + 2 * t + e;
+                        tab[nt][e] = tc < p.mc ? xs_tab[gi * p.mc + tc] : make_int2(0, 0);
+                    }
+                }
+
+                mbar_wait(&bars[s], parity);
+                const uint8_t* blk = ring + s * kW4BlockBytes;
+                if (p.dbg & 1) {
+                    acc[0][0][0] += __uint_as_float(*reinterpret_cast<const uint32_t*>(blk + lane * 4)) * 1e-30f;
+                } else {
+                    int ah[2][NT][4], al[2][NT][4];
+    #pragma unroll
+                    for (int tt = 0; tt < 2; ++tt)
+    #pragma unroll
+                        for (int nt = 0; nt < NT; ++nt)
+    #pragma unroll
+                            for (int c = 0; c < 4; ++c) ah[tt][nt][c] = al[tt][nt][c] = 0;
+    #pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint4 wv[2];
+    #pragma unroll
+                        for (int tt = 0; tt < 2; ++tt)
+                            wv[tt] = *reinterpret_cast<const uint4*>(blk + ((tt * 2 + hh) * 32 + lane) * 16);
+    #pragma unroll
+                        for (int jp = 0; jp < 2; ++jp) {
+                            const int j = hh * 2 + jp;   // k-step 0..3
+    #pragma unroll
+                            for (int tt = 0; tt < 2; ++tt) {   // the two 16-row tiles interleave: independent chains
+                                const uint32_t w0 = jp ? wv[tt].z : wv[tt].x;
+                                const uint32_t w1 = jp ? wv[tt].w : wv[tt].y;
+                                const uint32_t a[4] = {w0 & 0x0f0f0f0fu, w0 & 0xf0f0f0f0u, w1 & 0x0f0f0f0fu,
+                                                       w1 & 0xf0f0f0f0u};
+    #pragma unroll
+                                for (int nt = 0; nt < NT; ++nt) {
+                                    const uint4 vh = bh[nt][j >> 1], vl = bl[nt][j >> 1];
+                                    imma_u8s8(ah[tt][nt], a, (j & 1) ? vh.z : vh.x, (j & 1) ? vh.w : vh.y);
+                                    imma_u8u8(al[tt][nt], a, (j & 1) ? vl.z : vl.x, (j & 1) ? vl.w : vl.y);
+                                }
+                            }
+                        }
+                    }
+                    // exact integer group result, then one fp32 multiply-add per element
+    #pragma unroll
+                    for (int tt = 0; tt < 2; ++tt) {
+                        const __half2 sc = *reinterpret_cast<const __half2*>(blk + kW4ScaleOff + (tt * 8 + g) * 4);
+                        const int zz = blk[kW4ZeroOff + tt * 8 + g];
+                        const int z_lo = zz & 0xF, z_hi16 = zz & 0xF0;          // zero of row g ; 16 * zero of row g+8
+                        const float s_lo = __low2float(sc), s_hi = __high2float(sc) * 0.0625f;
+    #pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) {
+    #pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const int2 tb = tab[nt][c & 1];
+                                const int zc = (c >> 1) ? z_hi16 : z_lo;
+                                const int r = ah[tt][nt][c] * 256 + al[tt][nt][c] - zc * tb.x;
+                                const float f = ((c >> 1) ? s_hi : s_lo) * __int_as_float(tb.y);
+                                acc[tt][nt][c] = fmaf((float)r, f, acc[tt][nt][c]);
+                            }
                         }
                     }
                 }
@@ -329,8 +397,15 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
         for (int tt = 0; tt < 2; ++tt)
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-                const int tok = nt * 8 + 2 * t;
                 const int row = tt * 16 + g;
+                if constexpr (PACK) {   // lane t holds token t: acc[.][0][0] = row g, acc[.][0][2] = row g + 8
+                    if (t < RT) {
+                        myred[t * 32 + row] = acc[tt][0][0];
+                        myred[t * 32 + row + 8] = acc[tt][0][2];
+                    }
+                    continue;
+                }
+                const int tok = nt * 8 + 2 * t;
                 if (RT == NT * 8 || tok < RT) {
                     myred[tok * 32 + row] = acc[tt][nt][0];
                     myred[(tok + 1) * 32 + row] = acc[tt][nt][1];
@@ -443,12 +518,12 @@ static int v3_num_sms() {
 
 constexpr int kV3Budget = 231000;   // one CTA per SM (227 KB usable + 1 KB reserved)
 
-template <int NT, bool NORM, int WARPS, int SUBS, int STAGES, int RT>
+template <int NT, bool NORM, int WARPS, int SUBS, int STAGES, int RT, bool PACK>
 static cudaError_t launch_v3_t(const W4Params& p, int smem, bool pdl, cudaStream_t stream) {
     const int tiles = p.N / 32;
     const int want = (tiles + SUBS - 1) / SUBS;
     const int grid = want < v3_num_sms() ? want : v3_num_sms();
-    return launch(k_w4a16_v3<NT, NORM, WARPS, SUBS, STAGES, RT>, dim3(grid), dim3(WARPS * SUBS * 32), (size_t)smem, stream,
+    return launch(k_w4a16_v3<NT, NORM, WARPS, SUBS, STAGES, RT, PACK>, dim3(grid), dim3(WARPS * SUBS * 32), (size_t)smem, stream,
                   pdl, p);
 }
 
@@ -457,8 +532,14 @@ static bool v3_try(const W4Params& p, bool pdl, cudaStream_t stream, cudaError_t
     const int G = p.K / kW4GroupK;
     const int smem = V3Smem<NT, WARPS, SUBS, STAGES, RT>::kBytes + v3_stage_bytes(p.mc, p.K);
     if (G > 8 * WARPS * SUBS || smem > kV3Budget || p.mc > RT) return false;   // 8 = kMaxNg
-    *err = p.ln_w ? launch_v3_t<NT, true, WARPS, SUBS, STAGES, RT>(p, smem, pdl, stream)
-                  : launch_v3_t<NT, false, WARPS, SUBS, STAGES, RT>(p, smem, pdl, stream);
+    static const bool no_one = getenv("ZL_W4_NO_ONE") != nullptr;
+    if (NT == 1 && RT == NT * 8 && p.mc <= 4 && !no_one) {
+        *err = p.ln_w ? launch_v3_t<NT, true, WARPS, SUBS, STAGES, RT, NT == 1 && RT == NT * 8>(p, smem, pdl, stream)
+                      : launch_v3_t<NT, false, WARPS, SUBS, STAGES, RT, NT == 1 && RT == NT * 8>(p, smem, pdl, stream);
+        return true;
+    }
+    *err = p.ln_w ? launch_v3_t<NT, true, WARPS, SUBS, STAGES, RT, false>(p, smem, pdl, stream)
+                  : launch_v3_t<NT, false, WARPS, SUBS, STAGES, RT, false>(p, smem, pdl, stream);
     return true;
 }
 
@@ -524,6 +605,13 @@ cudaError_t prepare_w4_v3() {
     e = cudaFuncSetAttribute(k_w4a16_v3<NT, NORM, W, SB, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                              kV3Budget);                                                                        \
     if (e != cudaSuccess) return e;
+#define ZL_SET1(NORM, W, SB, ST)                                                                               \
+    e = cudaFuncSetAttribute(k_w4a16_v3<1, NORM, W, SB, ST, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             kV3Budget);                                                                        \
+    if (e != cudaSuccess) return e;
+    ZL_SET1(false, 8, 2, 5) ZL_SET1(true, 8, 2, 5) ZL_SET1(false, 8, 2, 4) ZL_SET1(true, 8, 2, 4)
+    ZL_SET1(false, 16, 1, 4) ZL_SET1(true, 16, 1, 4)
+#undef ZL_SET1
 #define ZL_SET2(NORM, W, SB, ST)                                                                               \
     e = cudaFuncSetAttribute(k_w4a16_v3<1, NORM, W, SB, ST, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                              kV3Budget);                                                                        \
