@@ -1,0 +1,13 @@
+#!/bin/bash
+timeout 600 python -m pytest tests/test_w4a16_int_gpu.py tests/test_llama_gpu.py -m gpu -q -x --timeout 120 --timeout-method thread -p no:cacheprovider 2>&1 | tail -3
+run() { timeout 300 python bench.py --steps 64 --warmup 4 --no-cpu-baseline --requests 0 $2 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    try: d=json.loads(l)
+    except Exception: print(l.strip()[:300]); continue
+    print('$1', round(d['value'],1), 'tok/s', round(d['ms_per_step'],4), 'ms', 'e2e', round(d['e2e']['value'],1), 'gemm us/launch', round(d['roofline']['us_per_launch'],2), 'frac', round(d['roofline']['frac'],3))
+"; }
+run "pack2 B=1" ""
+run "pack2 B=2" "--batch 2"
+run "pack2 B=4" "--batch 4"
+ZL_W4_DEBUG=10 LAYERS=4 timeout 200 python tools/trace_step.py 2>&1 | tail -12

@@ -39,12 +39,30 @@ st = torch.cuda.ExternalStream(dec2.stream())
 e0.record(st)
 dec2.step_device(1)
 e1.record(st)
+dec2.step_device(1)     # second step: shows the step boundary (head of step 2 after the tail of step 1)
 dec2.sync()
 t = trace.cpu().numpy()
 n = int(t[0])
 rec = t[8:8 + n * 16].reshape(n, 16)
 rec = rec[np.argsort(rec[:, 0])]
 t0 = rec[0, 0]
+dense = rec[rec[:, 15] == 0xD]
+gemm_all = rec[rec[:, 15] != 0xD]
+if len(dense):
+    d = dense[0]
+    before = gemm_all[gemm_all[:, 0] < d[0]]
+    after = gemm_all[gemm_all[:, 2] > d[3]]
+    last_end = max(x for x in before[-1] if x > 1000) if len(before) else d[0]
+    print("TAIL of step 1: last layer GEMM end -> lm_head entry %+.2f us, wait_done %+.2f, lm_head CTA0 end %+.2f ; "
+          "next step first qkv wait_done %+.2f us after lm_head CTA0 end"
+          % ((d[0] - last_end) / 1e3, (d[2] - last_end) / 1e3, (d[3] - last_end) / 1e3,
+             ((after[0][2] - d[3]) / 1e3) if len(after) else float("nan")))
+if len(dense):
+    hd = t[:8]
+    print("      lm_head last CTA done %+.2f us after last GEMM end; k_advance (after the graph) %+.2f ; next step k_lens_from_pos %+.2f"
+          % ((hd[5] - last_end) / 1e3, (hd[2] - last_end) / 1e3, (hd[1] - last_end) / 1e3))
+rec = gemm_all[: 4 * layers]
+n = len(rec)
 print("step %.1f us, %d GEMM launches, %d layers" % (e0.elapsed_time(e1) * 1e3, n, layers))
 names = ["qkv", "o", "gate_up", "down"]
 prev_end = 0.0

@@ -16,6 +16,8 @@
 #include <string>
 #include <vector>
 
+extern unsigned long long* g_w4_trace;   // debug timeline buffer (zl_w4_set_trace)
+
 namespace {
 
 struct Staged {
@@ -107,14 +109,17 @@ int dmalloc(void** p, size_t bytes) {
     return ZL_OK;
 }
 
-__global__ void k_lens_from_pos(const int32_t* __restrict__ pos, int32_t* __restrict__ lens, int B) {
+__global__ void k_lens_from_pos(const int32_t* __restrict__ pos, int32_t* __restrict__ lens, int B,
+                                unsigned long long* trace) {
     pdl_trigger();
     pdl_wait();
+    if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[1] = globaltimer_ns();   // debug timeline: step start
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < B) lens[i] = pos[i] + 1;
 }
 __global__ void k_advance(int32_t* __restrict__ tokens, int32_t* __restrict__ pos, const int32_t* __restrict__ next,
-                          int B) {
+                          int B, unsigned long long* trace) {
+    if (trace && blockIdx.x == 0 && threadIdx.x == 0 && trace[2] == 0) trace[2] = globaltimer_ns();   // debug: first step end
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < B) {
         tokens[i] = next[i];
@@ -649,7 +654,7 @@ int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* p
         ZL_CHECK_LAUNCH();
     } else {
         ZL_CHECK_CUDA(launch(k_lens_from_pos, dim3(cdiv(B, 64)), dim3(64), 0, st, false, (const int32_t*)m->d_pos,
-                             m->d_lens, B));
+                             m->d_lens, B, g_w4_trace));
     }
     m->cur_tb = pf ? m->d_tb : m->d_iota;
     RCHECK(zl_rope_cos_sin(m->d_pos, m->cosb, m->sinb, B, d, c.rope_theta, c.rope_llama3_factor,
@@ -992,7 +997,7 @@ extern "C" int zl_llama_step_device(zl_llama_t* m, int B) {
         return ZL_ERR_STATE;
     }
     RCHECK(run_step(m, B));
-    k_advance<<<cdiv(B, 64), 64, 0, m->stream>>>(m->d_tokens, m->d_pos, m->d_next, B);
+    k_advance<<<cdiv(B, 64), 64, 0, m->stream>>>(m->d_tokens, m->d_pos, m->d_next, B, g_w4_trace);
     ZL_CHECK_LAUNCH();
     m->cur_max_len += 1;
     return ZL_OK;

@@ -281,7 +281,7 @@ __global__ void k_gather_16(const uint16_t* __restrict__ src, const int32_t* __r
 }
 }  // namespace zl
 
-static unsigned long long* g_w4_trace = nullptr;
+unsigned long long* g_w4_trace = nullptr;   // shared with dense_gemm.cu (per-launch timeline records)
 extern "C" int zl_w4_set_trace(void* buf) {
     g_w4_trace = static_cast<unsigned long long*>(buf);
     return ZL_OK;

@@ -66,6 +66,82 @@ __device__ __forceinline__ void sub_barrier(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// PACK block math for NB blocks of one warp at once (NB = 2: two independent dependency chains interleave).
+template <int NB>
+__device__ __forceinline__ void pack_blocks(const W4Params& p, const uint8_t* ring, uint64_t* bars, const uint8_t* xs_hi,
+                                            const uint8_t* xs_lo, const int2* xs_tab, int row_b, const int* slot,
+                                            const uint32_t* parity, const int* gi, int g, int t, int lane,
+                                            float (&acc)[2][1][4]) {
+    // B fragment column n = g carries token g>>1, digit g&1 (0: high, 1: low); 32 contiguous bytes per lane
+    uint4 bv[NB][2];
+    int2 tb[NB];
+    const int tok = g >> 1;
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+        if (tok < p.mc) {
+            const uint8_t* pp = ((g & 1) ? xs_lo : xs_hi) + tok * row_b + gi[u] * 128 + t * 32;
+            bv[u][0] = *reinterpret_cast<const uint4*>(pp);
+            bv[u][1] = *reinterpret_cast<const uint4*>(pp + 16);
+        } else {
+            bv[u][0] = bv[u][1] = make_uint4(0, 0, 0, 0);
+        }
+        // C columns (2t, 2t+1) = (high, low) digit sums of token t: this lane finishes token t
+        tb[u] = t < p.mc ? xs_tab[gi[u] * p.mc + t] : make_int2(0, 0);
+    }
+    const uint8_t* blk[NB];
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+        mbar_wait(&bars[slot[u]], parity[u]);
+        blk[u] = ring + slot[u] * kW4BlockBytes;
+    }
+    int cc[NB][2][4];
+#pragma unroll
+    for (int u = 0; u < NB; ++u)
+#pragma unroll
+        for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) cc[u][tt][c] = 0;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        uint4 wv[NB][2];
+#pragma unroll
+        for (int u = 0; u < NB; ++u)
+#pragma unroll
+            for (int tt = 0; tt < 2; ++tt)
+                wv[u][tt] = *reinterpret_cast<const uint4*>(blk[u] + ((tt * 2 + hh) * 32 + lane) * 16);
+#pragma unroll
+        for (int jp = 0; jp < 2; ++jp) {
+            const int j = hh * 2 + jp;   // k-step 0..3
+#pragma unroll
+            for (int tt = 0; tt < 2; ++tt) {
+#pragma unroll
+                for (int u = 0; u < NB; ++u) {
+                    const uint32_t w0 = jp ? wv[u][tt].z : wv[u][tt].x;
+                    const uint32_t w1 = jp ? wv[u][tt].w : wv[u][tt].y;
+                    const uint32_t a[4] = {w0 & 0x0f0f0f0fu, w0 & 0xf0f0f0f0u, w1 & 0x0f0f0f0fu, w1 & 0xf0f0f0f0u};
+                    const uint4 v = bv[u][j >> 1];
+                    imma_u8s8(cc[u][tt], a, (j & 1) ? v.z : v.x, (j & 1) ? v.w : v.y);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {   // blocks in k order: the fp32 accumulation order does not depend on NB
+        const float sgf = __int_as_float(tb[u].y);
+#pragma unroll
+        for (int tt = 0; tt < 2; ++tt) {
+            const __half2 sc = *reinterpret_cast<const __half2*>(blk[u] + kW4ScaleOff + (tt * 8 + g) * 4);
+            const int zz = blk[u][kW4ZeroOff + tt * 8 + g];
+            const int z_lo = zz & 0xF, z_hi16 = zz & 0xF0;          // zero of row g ; 16 * zero of row g+8
+            const float s_lo = __low2float(sc), s_hi = __high2float(sc) * 0.0625f;
+            const int r0 = cc[u][tt][0] * 256 + cc[u][tt][1] - z_lo * tb[u].x;      // row g
+            const int r1 = cc[u][tt][2] * 256 + cc[u][tt][3] - z_hi16 * tb[u].x;    // row g + 8 (x16 folded in s_hi)
+            acc[tt][0][0] = fmaf((float)r0, s_lo * sgf, acc[tt][0][0]);
+            acc[tt][0][2] = fmaf((float)r1, s_hi * sgf, acc[tt][0][2]);
+        }
+    }
+}
+
 // PACK (mc <= 4): the MMA N dimension (8 columns) is mostly padding at tiny batch, so the two 8-bit digits of the
 // 16-bit activation mantissas share ONE IMMA: column 2i carries token i's high digit, column 2i+1 its low digit, both
 // signed (m = 256*hi' + lo', lo' = int8(m & 0xff), hi' = (m + 128) >> 8, |m| <= 2^14).  Half the IMMAs, half the B
@@ -242,7 +318,32 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
 #pragma unroll
                 for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
 
-        for (int i = 0; i < ng; ++i) {
+        int i = 0;
+        if constexpr (PACK) {
+            // two blocks in flight per warp: their smem loads, IMMA chains and epilogues interleave (the per-block
+            // dependency chain, not issue slots or HBM, is what a single block per warp leaves exposed)
+            for (; i + 2 <= ng; i += 2) {
+                int ss[2], gg[2];
+                uint32_t pp[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    ss[u] = c_slot;
+                    pp[u] = c_parity;
+                    if (++c_slot == STAGES) {
+                        c_slot = 0;
+                        c_parity ^= 1u;
+                    }
+                    gg[u] = g_begin + i + u;
+                }
+                pack_blocks<2>(p, ring, bars, xs_hi, xs_lo, xs_tab, row_b, ss, pp, gg, g, t, lane, acc);
+                __syncwarp();
+                if (lane == 0) {
+                    if (p_issued < total) issue_next();
+                    if (p_issued < total) issue_next();
+                }
+            }
+        }
+        for (; i < ng; ++i) {
             const int s = c_slot;
             const uint32_t parity = c_parity;
             if (++c_slot == STAGES) {
@@ -251,59 +352,7 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
             }
             const int gi = g_begin + i;
             if constexpr (PACK) {
-                // B fragment column n = g carries token g>>1, digit g&1 (0: high, 1: low); 32 contiguous bytes per lane
-                uint4 bv[2];
-                {
-                    const int tok = g >> 1;
-                    if (tok < p.mc) {
-                        const uint8_t* pp = ((g & 1) ? xs_lo : xs_hi) + tok * row_b + gi * 128 + t * 32;
-                        bv[0] = *reinterpret_cast<const uint4*>(pp);
-                        bv[1] = *reinterpret_cast<const uint4*>(pp + 16);
-                    } else {
-                        bv[0] = bv[1] = make_uint4(0, 0, 0, 0);
-                    }
-                }
-                // C columns (2t, 2t+1) = (high, low) digit sums of token t: this lane finishes token t
-                const int2 tb = t < p.mc ? xs_tab[gi * p.mc + t] : make_int2(0, 0);
-                mbar_wait(&bars[s], parity);
-                const uint8_t* blk = ring + s * kW4BlockBytes;
-                int cc[2][4];
-#pragma unroll
-                for (int tt = 0; tt < 2; ++tt)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) cc[tt][c] = 0;
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    uint4 wv[2];
-#pragma unroll
-                    for (int tt = 0; tt < 2; ++tt)
-                        wv[tt] = *reinterpret_cast<const uint4*>(blk + ((tt * 2 + hh) * 32 + lane) * 16);
-#pragma unroll
-                    for (int jp = 0; jp < 2; ++jp) {
-                        const int j = hh * 2 + jp;   // k-step 0..3
-#pragma unroll
-                        for (int tt = 0; tt < 2; ++tt) {
-                            const uint32_t w0 = jp ? wv[tt].z : wv[tt].x;
-                            const uint32_t w1 = jp ? wv[tt].w : wv[tt].y;
-                            const uint32_t a[4] = {w0 & 0x0f0f0f0fu, w0 & 0xf0f0f0f0u, w1 & 0x0f0f0f0fu,
-                                                   w1 & 0xf0f0f0f0u};
-                            const uint4 v = bv[j >> 1];
-                            imma_u8s8(cc[tt], a, (j & 1) ? v.z : v.x, (j & 1) ? v.w : v.y);
-                        }
-                    }
-                }
-                const float sgf = __int_as_float(tb.y);
-#pragma unroll
-                for (int tt = 0; tt < 2; ++tt) {
-                    const __half2 sc = *reinterpret_cast<const __half2*>(blk + kW4ScaleOff + (tt * 8 + g) * 4);
-                    const int zz = blk[kW4ZeroOff + tt * 8 + g];
-                    const int z_lo = zz & 0xF, z_hi16 = zz & 0xF0;          // zero of row g ; 16 * zero of row g+8
-                    const float s_lo = __low2float(sc), s_hi = __high2float(sc) * 0.0625f;
-                    const int r0 = cc[tt][0] * 256 + cc[tt][1] - z_lo * tb.x;      // row g
-                    const int r1 = cc[tt][2] * 256 + cc[tt][3] - z_hi16 * tb.x;    // row g + 8 (x16 folded in s_hi)
-                    acc[tt][0][0] = fmaf((float)r0, s_lo * sgf, acc[tt][0][0]);
-                    acc[tt][0][2] = fmaf((float)r1, s_hi * sgf, acc[tt][0][2]);
-                }
+                pack_blocks<1>(p, ring, bars, xs_hi, xs_lo, xs_tab, row_b, &s, &parity, &gi, g, t, lane, acc);
             } else {
                 // B fragments: 32 contiguous bytes of each piece per lane
                 uint4 bh[NT][2], bl[NT][2];
