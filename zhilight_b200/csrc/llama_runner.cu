@@ -479,6 +479,19 @@ static void prefetch_target(zl_llama* m, int l, int slot, int B, const void** pt
     *bytes = nb < prefetch_cap() ? nb : prefetch_cap();
 }
 
+// ZL_NO_PDL_MASK (experiments): launch these kernels with a full dependency instead of a programmatic one.
+// 1 qkv GEMM, 2 attention, 4 o GEMM, 8 gate_up GEMM, 16 down GEMM, 32 final norm, 64 lm_head, 128 argmax.
+// Default 70 = lm_head + o GEMM + attention: a PDL-launched lm_head measured 128 us slower per step than a normally
+// launched one (tools/gpu_tail.sh); early-launched o GEMM / attention CTAs cost another ~1 % each.
+static int no_pdl_mask() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ZL_NO_PDL_MASK");
+        v = e ? atoi(e) : 70;   // lm_head, o GEMM, attention: measured best (tools/gpu_pdlmask.sh: 640 -> 710 tok/s)
+    }
+    return v;
+}
+
 int w4_gemm(zl_llama* m, const void* x, int ldx, const W4Lin& w, const void* residual, void* y, int B, int epi,
             const void* ln_w, const Layer* rope_layer, int layer = -1, int slot = -1) {
     const auto& c = m->cfg;
@@ -505,7 +518,10 @@ int w4_gemm(zl_llama* m, const void* x, int ldx, const W4Lin& w, const void* res
     a.K = w.K;
     a.group_size = c.group_size;
     a.epilogue = epi;
-    a.pdl = c.use_pdl;
+    {
+        const int bit = slot == 0 ? 1 : slot == 2 ? 4 : slot == 3 ? 8 : slot == 4 ? 16 : 0;
+        a.pdl = (no_pdl_mask() & bit) ? 0 : c.use_pdl;
+    }
     a.ln_weight = ln_w;
     a.eps = c.eps;
     if (rope_layer) {
@@ -638,6 +654,8 @@ int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* p
     const int B = pf ? pf->n : n_tasks;   // rows (tokens) of every activation matrix in this launch sequence
     const int skip = debug_skip();
     const int D = c.dim_model, d = c.dim_head, dt = c.dtype, pdl = c.use_pdl;
+    const int npm = no_pdl_mask();
+    auto P = [&](int bit) { return (npm & bit) ? 0 : pdl; };
     cudaStream_t st = m->stream;
     const bool w4 = c.quant_type == 5 || c.quant_type == 6;
     const bool tp = c.tp_size > 1;
@@ -648,7 +666,7 @@ int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* p
     const float scale = 1.0f / sqrtf((float)d);   // attention.cpp:89
 
     // grid-barrier counter of the persistent kernel: zeroed first so that the kernel chain below stays kernel->kernel
-    if (m->d_mega_sync) ZL_CHECK_CUDA(cudaMemsetAsync(m->d_mega_sync, 0, 4, st));
+    if (m->d_mega_sync && c.fuse >= 3) ZL_CHECK_CUDA(cudaMemsetAsync(m->d_mega_sync, 0, 4, st));
     if (pf) {
         k_prefill_setup<<<8, 256, 0, st>>>(m->d_pos, m->d_tb, m->d_lens, m->d_mask, pf->task, pf->pos0, pf->n);
         ZL_CHECK_LAUNCH();
@@ -704,7 +722,7 @@ int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* p
                                        m->attn_ws_bytes, dt, pdl, st));
         } else if (!(skip & 1))
             RCHECK(zl_decode_attention(m->q, m->d_lens, L.k_addrs, L.v_addrs, nullptr, scale, len_bucket, m->ao, B, 1,
-                                       m->hq, m->hkv, d, 1, m->attn_ws, m->attn_ws_bytes, dt, pdl, st));
+                                       m->hq, m->hkv, d, 1, m->attn_ws, m->attn_ws_bytes, dt, P(2), st));
         if (w4) {
             if (skip & 4) {
             } else if (tp) {
@@ -754,16 +772,16 @@ int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* p
                                   1.f, 0, dt, pdl, st));
         }
     } else if (w4) {
-        RCHECK(zl_rmsnorm(m->h, m->ln_f, m->xn, B, D, c.eps, 1.f, dt, pdl, st));
+        RCHECK(zl_rmsnorm(m->h, m->ln_f, m->xn, B, D, c.eps, 1.f, dt, P(32), st));
     } else {
-        RCHECK(zl_add_rmsnorm(m->h, m->pend, m->ln_f, m->h, m->xn, B, D, c.eps, 1.f, 0, dt, pdl, st));
+        RCHECK(zl_add_rmsnorm(m->h, m->pend, m->ln_f, m->h, m->xn, B, D, c.eps, 1.f, 0, dt, P(32), st));
     }
     const int HB = pf ? 1 : B;   // rows that reach lm_head
     // vocab-parallel lm_head (embedding.cu:353-392): each rank owns vshard rows
     if (!(skip & 32))
-        RCHECK(zl_dense_gemm_skinny(m->xn, D, m->lm_head, nullptr, m->logits, HB, m->vshard, D, dt, ZL_F32, pdl, st));
+        RCHECK(zl_dense_gemm_skinny(m->xn, D, m->lm_head, nullptr, m->logits, HB, m->vshard, D, dt, ZL_F32, P(64), st));
     if (!tp) {
-        RCHECK(zl_argmax(m->logits, m->d_next, HB, m->vshard, m->argmax_ws, zl_argmax_workspace_bytes(HB), pdl, st));
+        RCHECK(zl_argmax(m->logits, m->d_next, HB, m->vshard, m->argmax_ws, zl_argmax_workspace_bytes(HB), P(128), st));
     } else {
         // instead of all-gathering (B, V) logits, exchange one {value, index} candidate per token
         const int stride = ((HB * 8 + 15) / 16) * 2;   // int2 records per rank slot (16-byte multiple)

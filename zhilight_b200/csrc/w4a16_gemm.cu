@@ -366,6 +366,7 @@ extern "C" int zl_w4a16_gemm_fused(const zl_w4_fused_args_t* a, zl_stream_t stre
             p.dbg = dbg;
         }
         p.trace = g_w4_trace;
+        if (p.dbg & 32) p.ln_w = nullptr;   // timing probe: drop the fused RMSNorm (results are wrong)
         p.pf_ptr = static_cast<const uint8_t*>(a->prefetch_ptr);
         p.pf_bytes = a->prefetch_bytes;
         if (a->variant == kW4VariantInt) {
