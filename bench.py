@@ -195,11 +195,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tp-int8", action="store_true", help="int8 group-32 payload for the TP all-reduce")
     ap.add_argument("--requests", type=int, default=32, help="requests for the TTFT/TPOT p50 (0 = skip)")
+    ap.add_argument("--quant", choices=["default", "int8", "fp8"], default="default",
+                    help="default: the model's BASELINE quantisation (GPTQ int4 for 8B, bf16 for 1B); int8 / fp8: W8A8 Linear rows")
     ap.add_argument("--fuse", type=int, default=2, help="0: one kernel per reference op; 1: +RMSNorm fused; 2: +qkv RoPE/KV epilogue")
     args = ap.parse_args()
 
     cfg = model_cfg(args.model)
     quant_name = "bf16" if args.model == "llama-3.2-1b" else "gptq-int4-g128-sym"
+    if args.quant != "default":
+        quant_name = {"int8": "w8a8-int8 (AutoInt8)", "fp8": "w8a8-fp8-e4m3"}[args.quant]
     workload = "%s %s greedy decode, batch=%d, prompt=%d, new=%d" % (args.model, quant_name, args.batch, args.prompt,
                                                                      args.steps)
     if args.impl == "reference":
@@ -224,10 +228,11 @@ def main():
     build.build()
 
     from zhilight_b200 import dist as zdist
-    dense = args.model == "llama-3.2-1b"
+    dense = args.model == "llama-3.2-1b" or args.quant != "default"   # every non-W4 Linear path reports k_dense/k_w8a8
+    qtype = {"default": 0 if args.model == "llama-3.2-1b" else 5, "int8": 2, "fp8": 7}[args.quant]
     W = max(args.warmup, 3)
     max_seq = args.prompt + 2 * W + 2 * args.steps + 16
-    dec = LlamaDecoder(quant_type=0 if dense else 5, group_size=128, sym=True, dtype="bf16" if dense else "f16",
+    dec = LlamaDecoder(quant_type=qtype, group_size=128, sym=True, dtype="bf16" if args.model == "llama-3.2-1b" else "f16",
                        max_batch=args.batch, max_seq=max_seq, use_pdl=not args.no_pdl, use_graph=not args.no_graph, fuse=args.fuse,
                        tp_rank=rank, tp_size=world, tp_int8=args.tp_int8,
                        prefill_chunk=32 if (world == 1 and args.requests > 0) else 0, **cfg)
@@ -304,7 +309,7 @@ def main():
             traffic = json.load(open(tp)).get("dram_bytes_per_launch") if (not dense and B == 1 and world == 1) else None
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_dense_skinny" if dense else "k_w4a16_v3 (integer IMMA; k_w4a16_v2 where its staging does not fit)",
+    roofline = {"bound": "hbm", "kernel": ("k_w8a8_skinny (+ activation quant)" if args.quant != "default" else "k_dense_skinny") if dense else "k_w4a16_v3 (integer IMMA; k_w4a16_v2 where its staging does not fit)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
                 "bytes_per_launch": g_bytes / g_launches, "us_per_launch": g_ms * 1e3 / iters / g_launches,
                 "traffic": traffic}
@@ -320,7 +325,8 @@ def main():
     out = {
         "metric": "decode tokens/s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": W, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
-        "vs_baseline": None, "dtype": "bf16" if dense else "f16 (W4A16: int4 weights, fp16 activations, fp32 accumulate)",
+        "vs_baseline": None, "dtype": {"int8": "int8 x int8 -> int32 (W8A8), f16 activations", "fp8": "e4m3 x e4m3 -> f32 (W8A8), f16 activations"}.get(
+            args.quant, "bf16" if dense else "f16 (W4A16: int4 weights, fp16 activations, fp32 accumulate)"),
         "data": "synthetic",
         "config": {"workload": workload, "parallelism": "single GPU" if world == 1 else "tp%d (one-shot NVLink all-reduce, %s payload)" % (world, "int8-g32" if args.tp_int8 else "fp16"),
                    "l2": "weights per step (%.2f GB) exceed L2 (126 MB); no explicit flush" % (weight_bytes / 1e9),

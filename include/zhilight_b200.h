@@ -136,7 +136,7 @@ int zl_gather_rows_16(const void* src, const int32_t* map, void* dst, int n, zl_
 
 /* ---- W8A8 Linear: SmoothQuant INT8 (Int8Linear, src/nn/linear/linear.cpp:432-636) and per-tensor FP8 e4m3
  * (Fp8Linear, linear.cpp:1612-1695) ---------------------------------------------------------------------- */
-enum { ZL_W8_INT8 = 0, ZL_W8_FP8 = 1 };
+enum { ZL_W8_INT8 = 0, ZL_W8_FP8 = 1, ZL_W8_FP8_ROWS = 2 /* fp8 with one f32 weight scale per output row */ };
 /* int8_op::quant_calc_scale (src/nn/quant/int8/quant_kernel.cu:15-103): per-token absmax quantisation,
  * scale[m] = absmax/127, q = int8(nearbyint(x * (127/absmax))).  x (M,K) f16/bf16 row stride ldx; q (M,K) int8. */
 int zl_int8_quant_per_token(const void* x, int ldx, void* q, float* scale, int M, int K, int dtype, int pdl,
@@ -289,7 +289,8 @@ typedef struct zl_llama_config {
     float eps, rope_theta;
     float rope_llama3_factor; /* <= 0: plain rope */
     float rope_low_freq_factor, rope_high_freq_factor, rope_orig_ctx;
-    int quant_type; /* model_config.hpp:132-144 QuantType: 0 none, 5 GPTQ, 6 AWQ */
+    int quant_type; /* model_config.hpp:132-144 QuantType: 0 none, 2 AutoInt8 (fp weights quantised per row at load),
+                     * 5 GPTQ, 6 AWQ, 7 FP8 (e4m3 weights + per-tensor weight_scale) */
     int group_size, sym;
     int dtype; /* ZL_F16 / ZL_BF16 (W4 paths are fp16-only like the reference, q_gemm_k_major.cu:989) */
     int max_batch, max_seq;

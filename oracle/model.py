@@ -61,6 +61,22 @@ class OracleLlama:
         return w
 
     def _linear(self, x, prefix):
+        if self.quant_type == 2:
+            # AutoInt8 (linear.cpp:521-550, 560-636): per-row int8 weights made at load, scale kept in T; per-token
+            # int8 activations; s32 GEMM; scale-back; bias added in T
+            if prefix not in self.w:
+                wq, ws = ops.int8_quant_per_token(_f32(self.sd[prefix + ".weight"], self.dtype))
+                self.w[prefix] = (wq, ops._t(ws, self.dtype))
+            wq, ws = self.w[prefix]
+            b = self.sd.get(prefix + ".bias")
+            return ops.int8_linear(x, wq, ws, self.dtype, None if b is None else _f32(b, self.dtype))
+        if self.quant_type == 7:
+            # Fp8Linear (linear.cpp:1660-1695): per-tensor dynamic e4m3 activations, e4m3 weights + scalar scale
+            if prefix not in self.w:
+                self.w[prefix] = ops.e4m3_decode(self.sd[prefix + ".weight"])
+            b = self.sd.get(prefix + ".bias")
+            return ops.fp8_linear(x, self.w[prefix], np.float32(self.sd[prefix + ".weight_scale"]).reshape(-1)[0],
+                                  self.dtype, None if b is None else _f32(b, self.dtype))
         y = np.asarray(x, F32) @ self._weight(prefix).T
         b = self.sd.get(prefix + ".bias")
         if b is not None:
@@ -151,6 +167,11 @@ def make_state_dict(cfg, quant_type=0, group_size=128, sym=False, seed=0, tied=F
             sd[prefix + ".qweight"] = r.integers(0, 2 ** 32, size=(k, n // 8), dtype=np.uint64).astype(np.uint32).view(np.int32)
             sd[prefix + ".qzeros"] = r.integers(0, 2 ** 32, size=(k // group_size, n // 8), dtype=np.uint64).astype(np.uint32).view(np.int32)
             sd[prefix + ".scales"] = (0.005 + 0.015 * r.random((k // group_size, n))).astype(np.float16)
+        elif quant_type == 7:
+            r = np.random.default_rng(s)
+            w8 = r.integers(0, 256, size=(n, k)).astype(np.uint8) & 0xBF     # exponent MSB cleared: |w| < 2, no NaN codes
+            sd[prefix + ".weight"] = w8
+            sd[prefix + ".weight_scale"] = np.array([0.02 + 0.02 * r.random()], dtype=np.float32)
         else:
             sd[prefix + ".weight"] = dense(n, k)
 

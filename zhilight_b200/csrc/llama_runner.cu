@@ -35,6 +35,10 @@ struct DenseLin {
     void* w = nullptr;
     void* bias = nullptr;
     int N = 0, K = 0;
+    // W8A8 (quant_type 2 / 7): 8-bit weights (N, K) + per-row scales; w is released
+    void* w8 = nullptr;
+    void* w_scale = nullptr;   // int8: (N) in the activation dtype (linear.cpp:541); fp8: (N) f32 rows
+    int w8_kind = -1;          // ZL_W8_INT8 or ZL_W8_FP8_ROWS
 };
 
 struct Layer {
@@ -87,6 +91,8 @@ struct zl_llama {
     bool mega_used = false;
     // chunked prefill (cfg.prefill_chunk > 0): activation buffers hold tok_cap = max(max_batch, chunk) tokens
     int tok_cap = 0;
+    void* xq = nullptr;           // W8A8: quantised activations of the Linear being run (tok_cap x max K bytes)
+    float* xs = nullptr;          //       their scales (tok_cap)
     int32_t* d_tb = nullptr;      // token -> task map of the chunk being prefilled
     const int32_t* cur_tb = nullptr;   // token -> task map of the launch sequence being enqueued (d_iota at decode)
     int8_t* d_mask = nullptr;     // (chunk, max_seq) causal mask of the chunk
@@ -143,6 +149,21 @@ __global__ void k_prefill_setup(int32_t* __restrict__ pos, int32_t* __restrict__
         if (threadIdx.x == 0) lens[task] = len_buf;
     }
 }
+
+template <typename T>
+__global__ void k_f32_to_t(const float* __restrict__ in, T* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = from_f32<T>(in[i]);
+}
+__global__ void k_fill_from_scalar(float* __restrict__ dst, int n, const float* __restrict__ scalar) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = *scalar;
+}
+__global__ void k_and_u32(uint32_t* __restrict__ p, size_t n, uint32_t mask) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] &= mask;
+}
+__global__ void k_set_f32(float* p, float v) { *p = v; }
 
 __global__ void k_iota(int32_t* p, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -335,6 +356,78 @@ int build_dense(zl_llama* m, const std::vector<std::string>& prefixes, const std
     return ZL_OK;
 }
 
+// quant_type 2 (AutoInt8, linear.cpp:521-550): the fp weight is quantised per output row at load with the same kernel
+// as the activations; the scale is kept in the activation dtype (functions::typecast, linear.cpp:541).
+int dense_to_int8(zl_llama* m, DenseLin* d) {
+    const auto& c = m->cfg;
+    float* sf = nullptr;
+    RCHECK(dmalloc(&d->w8, (size_t)d->N * d->K));
+    RCHECK(dmalloc((void**)&sf, (size_t)d->N * 4));
+    RCHECK(dmalloc(&d->w_scale, (size_t)d->N * 2));
+    RCHECK(zl_int8_quant_per_token(d->w, d->K, d->w8, sf, d->N, d->K, c.dtype, 0, m->stream));
+    if (c.dtype == ZL_F16)
+        k_f32_to_t<__half><<<cdiv(d->N, 256), 256, 0, m->stream>>>(sf, static_cast<__half*>(d->w_scale), d->N);
+    else
+        k_f32_to_t<__nv_bfloat16><<<cdiv(d->N, 256), 256, 0, m->stream>>>(sf, static_cast<__nv_bfloat16*>(d->w_scale), d->N);
+    ZL_CHECK_LAUNCH();
+    ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+    cudaFree(sf);
+    cudaFree(d->w);
+    d->w = nullptr;
+    d->w8_kind = ZL_W8_INT8;
+    m->weight_bytes += (double)d->N * d->K + (double)d->N * 2 - (double)d->N * d->K * 2;
+    return ZL_OK;
+}
+
+// quant_type 7 (Fp8Linear, linear.cpp:1612-1695): e4m3 weights + one f32 weight_scale per Linear.  Projections that
+// share an input are fused along N with their scalar scales expanded to one scale per output row.
+int build_fp8(zl_llama* m, const std::vector<std::string>& prefixes, const std::vector<int>& ns, int K, DenseLin* out) {
+    int N = 0;
+    for (int n : ns) N += n;
+    RCHECK(dmalloc(&out->w8, (size_t)N * K));
+    RCHECK(dmalloc(&out->w_scale, (size_t)N * 4));
+    int off = 0;
+    bool any_bias = false;
+    for (size_t i = 0; i < prefixes.size(); ++i) {
+        const Staged* w = find(m, prefixes[i] + ".weight");
+        const Staged* ws = find(m, prefixes[i] + ".weight_scale");
+        if (!w || w->rows != ns[i] || w->cols != K || w->elem != 1 || !ws || ws->elem != 4) {
+            zl_set_last_error(__FILE__, __LINE__, ("missing/ill-shaped fp8 weight or weight_scale " + prefixes[i]).c_str());
+            return ZL_ERR_STATE;
+        }
+        ZL_CHECK_CUDA(cudaMemcpyAsync((char*)out->w8 + (size_t)off * K, w->ptr, (size_t)ns[i] * K, cudaMemcpyDeviceToDevice,
+                                      m->stream));
+        k_fill_from_scalar<<<cdiv(ns[i], 256), 256, 0, m->stream>>>(static_cast<float*>(out->w_scale) + off, ns[i],
+                                                                     static_cast<const float*>(ws->ptr));
+        ZL_CHECK_LAUNCH();
+        if (find(m, prefixes[i] + ".bias")) any_bias = true;
+        off += ns[i];
+    }
+    if (any_bias) {
+        RCHECK(dmalloc(&out->bias, (size_t)N * 2));
+        ZL_CHECK_CUDA(cudaMemsetAsync(out->bias, 0, (size_t)N * 2, m->stream));
+        off = 0;
+        for (size_t i = 0; i < prefixes.size(); ++i) {
+            const Staged* b = find(m, prefixes[i] + ".bias");
+            if (b)
+                ZL_CHECK_CUDA(cudaMemcpyAsync((char*)out->bias + (size_t)off * 2, b->ptr, (size_t)ns[i] * 2,
+                                              cudaMemcpyDeviceToDevice, m->stream));
+            off += ns[i];
+        }
+    }
+    ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+    for (auto& p : prefixes) {
+        drop(m, p + ".weight");
+        drop(m, p + ".weight_scale");
+        drop(m, p + ".bias");
+    }
+    out->N = N;
+    out->K = K;
+    out->w8_kind = ZL_W8_FP8_ROWS;
+    m->weight_bytes += (double)N * K + (double)N * 4;
+    return ZL_OK;
+}
+
 int take_vector(zl_llama* m, const std::string& name, int n, void** out) {
     auto it = m->staged.find(name);
     if (it == m->staged.end() || (size_t)it->second.rows * it->second.cols != (size_t)n) {
@@ -363,11 +456,18 @@ int finalize_layer(zl_llama* m, int l) {
         RCHECK(build_w4(m, {p + "attn.attn_out"}, {D}, m->hq * d, false, &L.q_o));
         RCHECK(build_w4(m, gu, gu_n, D, true, &L.q_gu));
         RCHECK(build_w4(m, {p + "ff.w_out"}, {D}, m->ff, false, &L.q_down));
+    } else if (c.quant_type == 7) {
+        RCHECK(build_fp8(m, qkv, qkv_n, D, &L.d_qkv));
+        RCHECK(build_fp8(m, {p + "attn.attn_out"}, {D}, m->hq * d, &L.d_o));
+        RCHECK(build_fp8(m, gu, gu_n, D, &L.d_gu));
+        RCHECK(build_fp8(m, {p + "ff.w_out"}, {D}, m->ff, &L.d_down));
     } else {
         RCHECK(build_dense(m, qkv, qkv_n, D, &L.d_qkv));
         RCHECK(build_dense(m, {p + "attn.attn_out"}, {D}, m->hq * d, &L.d_o));
         RCHECK(build_dense(m, gu, gu_n, D, &L.d_gu));
         RCHECK(build_dense(m, {p + "ff.w_out"}, {D}, m->ff, &L.d_down));
+        if (c.quant_type == 2)
+            for (DenseLin* dl : {&L.d_qkv, &L.d_o, &L.d_gu, &L.d_down}) RCHECK(dense_to_int8(m, dl));
     }
     return ZL_OK;
 }
@@ -419,6 +519,12 @@ int alloc_runtime(zl_llama* m) {
     RCHECK(dmalloc((void**)&m->d_tokens, T * 4));
     RCHECK(dmalloc((void**)&m->d_pos, T * 4));
     RCHECK(dmalloc((void**)&m->d_lens, B * 4));
+    if (c.quant_type == 2 || c.quant_type == 7) {
+        int kmax = D > m->ff ? D : m->ff;
+        kmax = kmax > m->hq * d ? kmax : m->hq * d;
+        RCHECK(dmalloc(&m->xq, (size_t)T * kmax));
+        RCHECK(dmalloc((void**)&m->xs, (size_t)T * 4));
+    }
     if (c.prefill_chunk > 0) {
         RCHECK(dmalloc((void**)&m->d_tb, T * 4));
         RCHECK(dmalloc((void**)&m->d_mask, (size_t)c.prefill_chunk * c.max_seq));
@@ -643,6 +749,20 @@ static int debug_skip() {
     return v;
 }
 
+// One non-W4 Linear of the decode chain: dense (NormalLinear), or W8A8 = activation quant + fused 8-bit GEMM
+// (Int8Linear::forward / Fp8Linear::forward in two launches instead of three).
+int dense_or_w8(zl_llama* m, const void* x, const DenseLin& L, void* y, int B, int pdl) {
+    const auto& c = m->cfg;
+    cudaStream_t st = m->stream;
+    if (!L.w8) return zl_dense_gemm_skinny(x, L.K, L.w, L.bias, y, B, L.N, L.K, c.dtype, c.dtype, pdl, st);
+    if (L.w8_kind == ZL_W8_INT8) {
+        RCHECK(zl_int8_quant_per_token(x, L.K, m->xq, m->xs, B, L.K, c.dtype, pdl, st));
+        return zl_w8a8_gemm(m->xq, m->xs, L.w8, L.w_scale, c.dtype, L.bias, y, B, L.N, L.K, ZL_W8_INT8, c.dtype, pdl, st);
+    }
+    RCHECK(zl_fp8_quant_per_tensor(x, m->xq, m->xs, (size_t)B * L.K, c.dtype, pdl, st));
+    return zl_w8a8_gemm(m->xq, m->xs, L.w8, L.w_scale, ZL_F32, L.bias, y, B, L.N, L.K, ZL_W8_FP8_ROWS, c.dtype, pdl, st);
+}
+
 // pf != nullptr: one chunk of a prompt (tokens of ONE task at consecutive positions) instead of one token per task
 struct PrefillChunk {
     int task, pos0, n;
@@ -703,8 +823,7 @@ int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* p
             // residual of the previous layer's FFN is folded into this norm (block.cpp:139-141 + 131)
             RCHECK(zl_add_rmsnorm(m->h, l == 0 ? nullptr : m->pend, L.ln_attn, m->h, m->xn, B, D, c.eps, 1.f, 0, dt,
                                   pdl, st));
-            RCHECK(zl_dense_gemm_skinny(m->xn, D, L.d_qkv.w, L.d_qkv.bias, m->qkv, B, L.d_qkv.N, D, dt, dt, pdl,
-                                        st));
+            RCHECK(dense_or_w8(m, m->xn, L.d_qkv, m->qkv, B, pdl));
         }
         if (!(w4 && c.fuse >= 2) && !(skip & 64))
             RCHECK(zl_qkv_rope_append(m->cosb, m->sinb, m->qkv, m->q, m->cur_tb, m->d_pos, L.k_addrs, L.v_addrs, B,
@@ -749,15 +868,13 @@ int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* p
                 RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, m->h, m->h, B, ZL_EPI_RESIDUAL, nullptr, nullptr, l, 4));
             }
         } else {
-            RCHECK(zl_dense_gemm_skinny(m->ao, m->hq * d, L.d_o.w, L.d_o.bias, m->pend, B, D, m->hq * d, dt, dt, pdl,
-                                        st));
+            RCHECK(dense_or_w8(m, m->ao, L.d_o, m->pend, B, pdl));
             if (tp) RCHECK(zl_allreduce_one_shot(m->comm, m->pend, nullptr, m->pend, (size_t)B * D, dt, c.tp_int8, pdl, st));
             RCHECK(zl_add_rmsnorm(m->h, m->pend, L.ln_ff, m->h, m->xn, B, D, c.eps, 1.f, 0, dt, pdl, st));
-            RCHECK(zl_dense_gemm_skinny(m->xn, D, L.d_gu.w, L.d_gu.bias, m->gu, B, 2 * m->ff, D, dt, dt, pdl, st));
+            RCHECK(dense_or_w8(m, m->xn, L.d_gu, m->gu, B, pdl));
             RCHECK(zl_gate_mul(m->gu, 2 * m->ff, (char*)m->gu + (size_t)m->ff * 2, 2 * m->ff, m->act, m->ff, B,
                                m->ff, 0, dt, st));
-            RCHECK(zl_dense_gemm_skinny(m->act, m->ff, L.d_down.w, L.d_down.bias, m->pend, B, D, m->ff, dt, dt, pdl,
-                                        st));
+            RCHECK(dense_or_w8(m, m->act, L.d_down, m->pend, B, pdl));
             if (tp) RCHECK(zl_allreduce_one_shot(m->comm, m->pend, nullptr, m->pend, (size_t)B * D, dt, c.tp_int8, pdl, st));
         }
     }
@@ -834,13 +951,15 @@ extern "C" int zl_llama_create(const zl_llama_config_t* cfg, zl_llama_t** out) {
     ZL_CHECK_ARG(cfg->num_layers > 0 && cfg->dim_model > 0 && cfg->num_heads > 0 && cfg->num_kv_heads > 0);
     ZL_CHECK_ARG(cfg->dim_head > 0 && cfg->dim_ff > 0 && cfg->vocab_size > 0 && cfg->max_batch > 0 &&
                  cfg->max_seq > 0);
-    ZL_CHECK_SUPPORTED(cfg->quant_type == 0 || cfg->quant_type == 5 || cfg->quant_type == 6);
-    ZL_CHECK_SUPPORTED(cfg->quant_type == 0 || cfg->dtype == ZL_F16);   // "A must be half" q_gemm_k_major.cu:989
+    ZL_CHECK_SUPPORTED(cfg->quant_type == 0 || cfg->quant_type == 2 || cfg->quant_type == 5 || cfg->quant_type == 6 ||
+                       cfg->quant_type == 7);
+    ZL_CHECK_SUPPORTED(!(cfg->quant_type == 5 || cfg->quant_type == 6) || cfg->dtype == ZL_F16);
+    ZL_CHECK_SUPPORTED(!(cfg->quant_type == 2 || cfg->quant_type == 7) || cfg->tp_size == 1);   // "A must be half" q_gemm_k_major.cu:989
     ZL_CHECK_SUPPORTED(cfg->dtype == ZL_F16 || cfg->dtype == ZL_BF16);
     ZL_CHECK_SUPPORTED(cfg->tp_size >= 1 && cfg->tp_rank >= 0 && cfg->tp_rank < cfg->tp_size);
     ZL_CHECK_SUPPORTED(cfg->num_heads % cfg->tp_size == 0 && cfg->num_kv_heads % cfg->tp_size == 0 &&
                        cfg->dim_ff % cfg->tp_size == 0 && cfg->vocab_size % cfg->tp_size == 0);
-    ZL_CHECK_SUPPORTED(cfg->quant_type == 0 || cfg->group_size == zl::kW4GroupK);
+    ZL_CHECK_SUPPORTED(!(cfg->quant_type == 5 || cfg->quant_type == 6) || cfg->group_size == zl::kW4GroupK);
     ZL_CHECK_ARG(cfg->fuse >= 0 && cfg->fuse <= 3);
     ZL_CHECK_ARG(cfg->prefill_chunk >= 0 && cfg->prefill_chunk <= 32);
     ZL_CHECK_SUPPORTED(cfg->fuse < 2 || cfg->dim_head % 32 == 0);
@@ -876,13 +995,13 @@ extern "C" void zl_llama_destroy(zl_llama_t* m) {
     for (auto& L : m->layers) {
         for (void* p : {L.ln_attn, L.ln_ff, L.q_qkv.packed, L.q_qkv.bias, L.q_o.packed, L.q_o.bias, L.q_gu.packed,
                         L.q_down.packed, L.q_down.bias, L.q_qkv.packed_i, L.q_o.packed_i, L.q_gu.packed_i, L.q_down.packed_i, L.d_qkv.w, L.d_qkv.bias, L.d_o.w, L.d_o.bias, L.d_gu.w,
-                        L.d_gu.bias, L.d_down.w, L.d_down.bias, L.kbuf, L.vbuf, (void*)L.k_addrs, (void*)L.v_addrs})
+                        L.d_gu.bias, L.d_down.w, L.d_down.bias, L.d_qkv.w8, L.d_qkv.w_scale, L.d_o.w8, L.d_o.w_scale, L.d_gu.w8, L.d_gu.w_scale, L.d_down.w8, L.d_down.w_scale, L.kbuf, L.vbuf, (void*)L.k_addrs, (void*)L.v_addrs})
             if (p) cudaFree(p);
     }
     for (void* p : {m->emb, m->lm_head_tied ? nullptr : m->lm_head, m->ln_f, m->h, m->xn, m->qkv, m->q, m->ao, m->act,
                     m->pend, m->gu, (void*)m->logits, (void*)m->cosb, (void*)m->sinb, (void*)m->d_tokens,
                     (void*)m->d_pos, (void*)m->d_lens, (void*)m->d_next, (void*)m->d_iota, m->attn_ws, m->argmax_ws, (void*)m->d_mega_layers, (void*)m->d_mega_sync,
-                    (void*)m->d_mega_trace, (void*)m->d_tb, (void*)m->d_mask})
+                    (void*)m->d_mega_trace, (void*)m->d_tb, (void*)m->d_mask, m->xq, (void*)m->xs})
         if (p) cudaFree(p);
     if (m->h_stage) cudaFreeHost(m->h_stage);
     cudaStreamDestroy(m->stream);
@@ -954,6 +1073,22 @@ int stage_random_linear(zl_llama* m, const std::string& prefix, int K, int N, ui
         RCHECK(stage_random(m, prefix + ".qweight", K, N / 8, 4, 0, 0, 0, seed));
         RCHECK(stage_random(m, prefix + ".qzeros", G, N / 8, 4, 0, 0, 0, seed));
         RCHECK(stage_random(m, prefix + ".scales", G, N, 2, 2, 0.002f, 0.006f, seed));
+    } else if (c.quant_type == 7) {
+        // random e4m3 codes with the exponent MSB cleared (|w| < 2, no NaN encodings) and a per-tensor scale
+        RCHECK(stage_random(m, prefix + ".weight", N, K / 4, 4, 0, 0, 0, seed));
+        Staged& w = m->staged[prefix + ".weight"];
+        const size_t words = (size_t)N * K / 4;
+        k_and_u32<<<(unsigned)((words + 255) / 256), 256, 0, m->stream>>>(static_cast<uint32_t*>(w.ptr), words, 0xBFBFBFBFu);
+        ZL_CHECK_LAUNCH();
+        w.cols = K;
+        w.elem = 1;
+        Staged sc;
+        sc.rows = sc.cols = 1;
+        sc.elem = 4;
+        RCHECK(dmalloc(&sc.ptr, 4));
+        k_set_f32<<<1, 1, 0, m->stream>>>(static_cast<float*>(sc.ptr), 0.03f);
+        ZL_CHECK_LAUNCH();
+        m->staged[prefix + ".weight_scale"] = sc;
     } else {
         RCHECK(stage_random(m, prefix + ".weight", N, K, 2, 2, -0.035f, 0.035f, seed));   // ~ randn*0.02
     }
@@ -1085,15 +1220,16 @@ extern "C" int zl_llama_bench_gemms(zl_llama_t* m, int B, int iters, float* ms, 
                     nbytes += 2.0 * B * (D + L.q_qkv.N + m->hq * d + 2 * D + D + m->ff + m->ff + 2 * D);
                 }
             } else {
-                RCHECK(zl_dense_gemm_skinny(m->xn, D, L.d_qkv.w, L.d_qkv.bias, m->qkv, B, L.d_qkv.N, D, dt, dt, pdl, st));
-                RCHECK(zl_dense_gemm_skinny(m->ao, m->hq * d, L.d_o.w, L.d_o.bias, m->pend, B, D, m->hq * d, dt, dt,
-                                            pdl, st));
-                RCHECK(zl_dense_gemm_skinny(m->xn, D, L.d_gu.w, L.d_gu.bias, m->gu, B, 2 * m->ff, D, dt, dt, pdl, st));
-                RCHECK(zl_dense_gemm_skinny(m->act, m->ff, L.d_down.w, L.d_down.bias, m->pend, B, D, m->ff, dt, dt,
-                                            pdl, st));
-                if (it == 0)
-                    nbytes += 2.0 * ((double)L.d_qkv.N * D + (double)D * m->hq * d + 2.0 * m->ff * D + (double)D * m->ff) +
+                RCHECK(dense_or_w8(m, m->xn, L.d_qkv, m->qkv, B, pdl));
+                RCHECK(dense_or_w8(m, m->ao, L.d_o, m->pend, B, pdl));
+                RCHECK(dense_or_w8(m, m->xn, L.d_gu, m->gu, B, pdl));
+                RCHECK(dense_or_w8(m, m->act, L.d_down, m->pend, B, pdl));
+                if (it == 0) {
+                    // weight bytes: 2 per element dense, 1 (+ per-row scale) for W8A8
+                    const double wb = L.d_qkv.w8 ? 1.0 : 2.0;
+                    nbytes += wb * ((double)L.d_qkv.N * D + (double)D * m->hq * d + 2.0 * m->ff * D + (double)D * m->ff) +
                               2.0 * B * (D + L.d_qkv.N + m->hq * d + D + D + 2 * m->ff + m->ff + D);
+                }
             }
             if (it == 0) n_launch += 4;
         }

@@ -299,7 +299,8 @@ k_w8a8_skinny(const uint8_t* __restrict__ xq, const float* __restrict__ sx, cons
                 float v;
                 if constexpr (FP8) {
                     // cuBLASLt fp8: D = (scaleA * scaleB) * acc (+ bias), functions::Gemm with A/B scales
-                    const float s_w = *static_cast<const float*>(sw);
+                    // sw_f32 == 2: one scale per output row (several per-tensor-scaled projections fused along N)
+                    const float s_w = sw_f32 == 2 ? static_cast<const float*>(sw)[row] : *static_cast<const float*>(sw);
                     v = acc[nt][c] * (sx[0] * s_w);
                     if (bias) v += to_f32<T>(bias[row]);
                 } else {
@@ -423,14 +424,14 @@ extern "C" int zl_w8a8_gemm(const void* xq, const float* x_scale, const void* w,
                             int pdl, zl_stream_t stream) {
     ZL_CHECK_ARG(xq && x_scale && w && w_scale && y && M > 0 && N > 0 && K > 0);
     ZL_CHECK_ARG(dtype == ZL_F16 || dtype == ZL_BF16);
-    ZL_CHECK_ARG(kind == ZL_W8_INT8 || kind == ZL_W8_FP8);
+    ZL_CHECK_ARG(kind == ZL_W8_INT8 || kind == ZL_W8_FP8 || kind == ZL_W8_FP8_ROWS);
     ZL_CHECK_ARG(w_scale_dtype == ZL_F32 || w_scale_dtype == dtype);
     ZL_CHECK_ARG(kind == ZL_W8_INT8 || w_scale_dtype == ZL_F32);
     ZL_CHECK_SUPPORTED(K % 64 == 0);
     ZL_CHECK_ARG((reinterpret_cast<uintptr_t>(xq) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0);
     const uint8_t* xq8 = static_cast<const uint8_t*>(xq);
     const uint8_t* w8 = static_cast<const uint8_t*>(w);
-    const int sw_f32 = w_scale_dtype == ZL_F32;
+    const int sw_f32 = kind == ZL_W8_FP8_ROWS ? 2 : (w_scale_dtype == ZL_F32 ? 1 : 0);
     for (int m0 = 0; m0 < M; m0 += 32) {
         const int mc = (M - m0) < 32 ? (M - m0) : 32;
         const bool p = pdl != 0 && m0 == 0;
@@ -440,10 +441,10 @@ extern "C" int zl_w8a8_gemm(const void* xq, const float* x_scale, const void* w,
     e = launch_w8<TT, F8>(xq8 + (size_t)m0 * K, sx, w8, w_scale, sw_f32, static_cast<const TT*>(bias),              \
                           static_cast<TT*>(y) + (size_t)m0 * N, mc, N, K, p, stream)
         if (dtype == ZL_F16) {
-            if (kind == ZL_W8_FP8) ZL_W8_GO(__half, true);
+            if (kind != ZL_W8_INT8) ZL_W8_GO(__half, true);
             else ZL_W8_GO(__half, false);
         } else {
-            if (kind == ZL_W8_FP8) ZL_W8_GO(__nv_bfloat16, true);
+            if (kind != ZL_W8_INT8) ZL_W8_GO(__nv_bfloat16, true);
             else ZL_W8_GO(__nv_bfloat16, false);
         }
 #undef ZL_W8_GO
