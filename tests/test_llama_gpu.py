@@ -1,6 +1,8 @@
 """GPU parity: the whole decode step (driver + every kernel) against the CPU oracle model on small
 synthetic checkpoints -- the round trip a user of zhilight.LLaMA / DynamicBatchGenerator sees:
 state_dict in (HF-GPTQ layout), (token, position) per task in, logits / greedy tokens out."""
+import os
+
 import numpy as np
 import pytest
 
@@ -154,12 +156,12 @@ def test_persistent_kernel_matches_kernel_chain(lib, cuda, cfg, max_batch):
 
 
 # W4: the M = 32 passes run the fp16-HMMA kernel (fp16 dequant, fp32 accumulate), not the exact-integer M <= 16 kernel
-@pytest.mark.parametrize("quant,dtype,tol", [(5, "f16", 5e-3), (0, "f16", 3e-3), (0, "bf16", 2e-2)])
-def test_chunked_prefill_matches_token_by_token_oracle(lib, cuda, quant, dtype, tol):
+@pytest.mark.parametrize("quant,dtype,tol,cfg", [(5, "f16", 5e-3, TINY128), (5, "f16", 5e-3, TINY), (0, "f16", 3e-3, TINY),
+                                                 (0, "bf16", 2e-2, TINY)], ids=["gptq-d128", "gptq-d64", "f16", "bf16"])
+def test_chunked_prefill_matches_token_by_token_oracle(lib, cuda, quant, dtype, tol, cfg):
     """zl_llama_prefill (chunks of <= 32 tokens through the M = chunk GEMMs and causal len_q = chunk attention) must
     leave the same KV state and produce the same next-token logits as feeding the prompt one token at a time."""
     from zhilight_b200.llama import LlamaDecoder
-    cfg = TINY128 if quant == 5 else TINY
     sd = omodel.make_state_dict(cfg, quant, 128, False, seed=9, dtype=dtype)
     dec = LlamaDecoder(quant_type=quant, dtype=dtype, max_batch=2, max_seq=128, prefill_chunk=32, **cfg)
     dec.load_state_dict(sd)
@@ -206,3 +208,36 @@ def test_w8a8_decode_matches_oracle(lib, cuda, quant, dtype, tol):
     for nxt, logits, ref in _run(TINY, quant, dtype, steps=4):
         assert np.isfinite(logits).all()
         assert rel_l2(logits, ref) <= tol
+
+
+@pytest.mark.parametrize("cfg", [TINY128, TINY], ids=["d128", "d64-2kvheads"])
+def test_dual_stream_prefill_matches_single_stream(lib, cuda, monkeypatch, cfg):
+    """the two-half / two-stream prefill pipeline (compute stream + reduce stream, events) must produce
+    the same KV state and logits as the single-stream chunked prefill; on one GPU the 'reduce' is the residual add."""
+    from zhilight_b200.llama import LlamaDecoder
+    sd = omodel.make_state_dict(cfg, 5, 128, False, seed=13)
+    rng = np.random.default_rng(6)
+    prompt = rng.integers(0, cfg["vocab_size"], size=84).astype(np.int32)       # chunks 32, 32, 20 -> halves 16/16, 16/4
+    outs = []
+    for dual in ("0", "1"):
+        monkeypatch.setenv("ZL_PREFILL_DUAL", dual)
+        dec = LlamaDecoder(quant_type=5, max_batch=1, max_seq=128, prefill_chunk=32,
+                           fuse=int(os.environ.get("ZL_TEST_FUSE", "2")), **cfg)
+        dec.load_state_dict(sd)
+        nxt, logits = dec.prefill(0, prompt[:int(os.environ.get("ZL_TEST_PROMPT", "84"))], want_logits=True)
+        tok, pos = np.array([nxt], np.int32), np.array([int(os.environ.get("ZL_TEST_PROMPT", "84"))], np.int32)
+        steps = [logits.copy()]
+        for _ in range(3):
+            t2, lg = dec.decode(tok, pos, want_logits=True)
+            steps.append(lg.copy())
+            tok, pos = t2, pos + 1
+        dec.close()
+        outs.append(steps)
+    for a, b in zip(*outs):
+        assert np.isfinite(a).all()
+        # M = 32 chunks vs two M = 16 halves run different GEMM kernels (fp16-HMMA vs exact-integer): fp16-level agreement
+        assert rel_l2(b, a) <= 3e-3
+    orc = omodel.OracleLlama(cfg, sd, 5, 128, False, "f16", fuse_norm=True)
+    for p, t in enumerate(prompt[:int(os.environ.get("ZL_TEST_PROMPT", "84"))]):
+        ref = orc.decode(np.array([t]), [p])
+    assert rel_l2(outs[1][0], ref) <= 5e-3

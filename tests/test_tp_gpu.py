@@ -82,6 +82,26 @@ def _worker(rank, ws, port, q):
             res["tp_quant%d" % quant] = (float(worst), bool(agree))
             dec.close()
             c2.close()
+        # TP chunked prefill: with tp_size > 1 the two-half / two-stream pipeline is on by default --
+        # the reduce stream all-reduces one half's partial sums while the compute stream runs the other half
+        sd = omodel.make_state_dict(TINY, 5, 128, False, seed=4)
+        dec = LlamaDecoder(quant_type=5, max_batch=1, max_seq=96, tp_rank=rank, tp_size=ws, prefill_chunk=32, **TINY)
+        c3 = zdist.TPComm(32 * TINY["dim_model"], rank, ws)
+        dec.set_comm(c3)
+        dec.load_state_dict(zdist.shard_state_dict(sd, rank, ws))
+        orc = omodel.OracleLlama(TINY, sd, 5, 128, False, "f16", fuse_norm=True)
+        prompt = np.random.default_rng(8).integers(0, TINY["vocab_size"], size=52).astype(np.int32)
+        nxt, logits = dec.prefill(0, prompt, want_logits=True)
+        for p_, t_ in enumerate(prompt):
+            ref = orc.decode(np.array([t_]), [p_])
+        vs = TINY["vocab_size"] // ws
+        res["tp_prefill"] = float(rel_l2(logits, ref[:, rank * vs:(rank + 1) * vs]))
+        nxt2, logits2 = dec.decode(np.array([int(np.argmax(ref[0]))], np.int32), np.array([len(prompt)], np.int32),
+                                   want_logits=True)
+        ref2 = orc.decode(np.array([int(np.argmax(ref[0]))]), [len(prompt)])
+        res["tp_prefill_then_decode"] = float(rel_l2(logits2, ref2[:, rank * vs:(rank + 1) * vs]))
+        dec.close()
+        c3.close()
         comm.close()
     except Exception as e:   # pragma: no cover
         import traceback
@@ -113,3 +133,4 @@ def test_tp_exchange_and_decode(lib, cuda, ws):
         assert res["vs_nccl"] < 2e-3, res
         assert res["tp_quant5"][0] < 3e-3 and res["tp_quant5"][1], res
         assert res["tp_quant0"][0] < 3e-3 and res["tp_quant0"][1], res
+        assert res["tp_prefill"] < 5e-3 and res["tp_prefill_then_decode"] < 5e-3, res

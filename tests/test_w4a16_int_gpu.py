@@ -52,8 +52,8 @@ def test_config1_1x4096x4096_int(lib, cuda, sym):
     assert rel_l2(y, ref) <= 4e-4
 
 
-@pytest.mark.parametrize("m", [1, 2, 3, 5, 8])
-@pytest.mark.parametrize("k,n", [(1024, 512), (4096, 6144), (14336, 4096), (4096, 4096), (4096 + 128, 96), (256, 64)])
+@pytest.mark.parametrize("m", [1, 2, 3, 5, 8, 12, 16])
+@pytest.mark.parametrize("k,n", [(1024, 512), (4096, 6144), (14336, 4096), (4096, 4096), (4096 + 128, 96), (256, 64), (256, 512)])
 def test_shapes_and_batches_int(lib, cuda, m, k, n):
     from zhilight_b200 import ops, _lib
     if not _lib.load().zl_w4_int_kernel_fits(m, n, k):
@@ -119,20 +119,21 @@ def test_epilogues_and_fused_norm_int(lib, cuda, m):
     assert rel_l2(y2, ref2) <= TOL
 
 
-def test_qkv_rope_epilogue_int(lib, cuda):
+@pytest.mark.parametrize("d,hq,hkv,k,t", [(128, 4, 2, 512, 3), (64, 4, 2, 256, 3), (64, 4, 2, 256, 16), (128, 4, 1, 512, 12),
+                                          (64, 2, 1, 256, 4)])
+def test_qkv_rope_epilogue_int(lib, cuda, d, hq, hkv, k, t):
+    """Batch sizes of every kernel variant (digit-packed <= 4, NT=1 <= 8, NT=2 <= 16) x both head sizes."""
     from zhilight_b200 import ops
-    d, hq, hkv, k = 128, 4, 2, 512
     n = (hq + 2 * hkv) * d
     rm = ops.qkv_rope_row_map(hq + 2 * hkv, d, cuda)
     w, packed_i, _, _ = _setup(cuda, k, n, False, 14, rm)
     _, _, packed_plain, _ = _setup(cuda, k, n, False, 14)
     g = torch.Generator().manual_seed(8)
-    t = 3
     x = torch.randn(t, k, generator=g).half().to(cuda)
-    pos = torch.tensor([0, 3, 7], dtype=torch.int32, device=cuda)
+    pos = torch.tensor([(5 * i) % 11 for i in range(t)], dtype=torch.int32, device=cuda)
     cos, sin = ops.rope_cos_sin(pos, d, 10000.0)
-    tb = torch.tensor([0, 1, 2], dtype=torch.int32, device=cuda)
-    pl = torch.tensor([0, 3, 7], dtype=torch.int32, device=cuda)
+    tb = torch.tensor([i % 3 for i in range(t)], dtype=torch.int32, device=cuda)
+    pl = torch.tensor([i // 3 for i in range(t)], dtype=torch.int32, device=cuda)     # (task, slot) pairs are unique
     kb = [torch.zeros(12, hkv, d, dtype=torch.float16, device=cuda) for _ in range(3)]
     vb = [torch.zeros(12, hkv, d, dtype=torch.float16, device=cuda) for _ in range(3)]
     q = ops.w4a16_gemm_fused(x, packed_i, n, k, epilogue=ops.EPI_QKV_ROPE, variant=1,

@@ -91,6 +91,10 @@ struct zl_llama {
     bool mega_used = false;
     // chunked prefill (cfg.prefill_chunk > 0): activation buffers hold tok_cap = max(max_batch, chunk) tokens
     int tok_cap = 0;
+    // dual-stream chunked prefill (EncoderLayer::dual_stream_encode, block.cpp:205-441): compute stream = m->stream
+    cudaStream_t reduce_stream = nullptr;
+    cudaEvent_t ev_o[2] = {nullptr, nullptr}, ev_r1[2] = {nullptr, nullptr}, ev_dn[2] = {nullptr, nullptr},
+                ev_r2[2] = {nullptr, nullptr};
     void* xq = nullptr;           // W8A8: quantised activations of the Linear being run (tok_cap x max K bytes)
     float* xs = nullptr;          //       their scales (tok_cap)
     int32_t* d_tb = nullptr;      // token -> task map of the chunk being prefilled
@@ -495,6 +499,10 @@ int alloc_runtime(zl_llama* m) {
     for (auto& L : m->layers) {
         RCHECK(dmalloc(&L.kbuf, kv_task * B));
         RCHECK(dmalloc(&L.vbuf, kv_task * B));
+        // never-written rows must be finite: masked keys still multiply their V rows by an exact 0, and with the
+        // dual-stream prefill one half's attention sees the other half's rows before they are appended
+        ZL_CHECK_CUDA(cudaMemsetAsync(L.kbuf, 0, kv_task * B, m->stream));
+        ZL_CHECK_CUDA(cudaMemsetAsync(L.vbuf, 0, kv_task * B, m->stream));
         RCHECK(dmalloc((void**)&L.k_addrs, sizeof(void*) * B));
         RCHECK(dmalloc((void**)&L.v_addrs, sizeof(void*) * B));
         k_ptr_table<<<1, 256, 0, m->stream>>>(L.k_addrs, (char*)L.kbuf, kv_task, B);
@@ -599,7 +607,7 @@ static int no_pdl_mask() {
 }
 
 int w4_gemm(zl_llama* m, const void* x, int ldx, const W4Lin& w, const void* residual, void* y, int B, int epi,
-            const void* ln_w, const Layer* rope_layer, int layer = -1, int slot = -1) {
+            const void* ln_w, const Layer* rope_layer, int layer = -1, int slot = -1, int row0 = 0, int force_no_pdl = 0) {
     const auto& c = m->cfg;
     zl_w4_fused_args_t a = {};
     a.x = x;
@@ -631,17 +639,19 @@ int w4_gemm(zl_llama* m, const void* x, int ldx, const W4Lin& w, const void* res
     a.ln_weight = ln_w;
     a.eps = c.eps;
     if (rope_layer) {
-        a.cos = m->cosb;
-        a.sin = m->sinb;
-        a.q_out = m->q;
-        a.token_batch = m->cur_tb;
-        a.placement = m->d_pos;
+        // row0: first token row of this call inside the step's activation matrices (dual-stream prefill halves)
+        a.cos = m->cosb + (size_t)row0 * c.dim_head;
+        a.sin = m->sinb + (size_t)row0 * c.dim_head;
+        a.q_out = (char*)m->q + (size_t)row0 * m->hq * c.dim_head * 2;
+        a.token_batch = m->cur_tb + row0;
+        a.placement = m->d_pos + row0;
         a.k_addrs = rope_layer->k_addrs;
         a.v_addrs = rope_layer->v_addrs;
         a.num_heads = m->hq;
         a.num_kv_heads = m->hkv;
         a.dim_head = c.dim_head;
     }
+    if (force_no_pdl) a.pdl = 0;
     return zl_w4a16_gemm_fused(&a, m->stream);
 }
 
@@ -769,6 +779,95 @@ struct PrefillChunk {
     bool last;   // run final norm + lm_head + pick on the chunk's last token
 };
 
+// ------------------------------------------------------------------------------------------------------------------
+// Dual-stream chunked prefill of a W4 model (EncoderLayer::impl::dual_stream_encode, src/nn/block/block.cpp:205-441):
+// the chunk's tokens are split in two halves that walk the layers as a 2-stage pipeline -- while the reduce stream
+// combines half A's row-parallel partial sums (NVLink all-reduce fused with the residual add; a plain residual add when
+// tp_size == 1), the compute stream already runs half B's GEMMs / attention.  The reference creates its second stream
+// and 2*num_split events on every forward (block.cpp:220-224, 260-267); here they live in the model object.
+//   compute: S1(h0) S1(h1) S3(h0) S3(h1) | next layer ...      S1 = qkv(+RoPE, KV append) -> attention -> o GEMM
+//   reduce :        R1(h0) R1(h1) R2(h0) R2(h1)                S3 = gate_up (SwiGLU) -> down GEMM ; R = reduce + residual
+// ------------------------------------------------------------------------------------------------------------------
+int ensure_dual_resources(zl_llama* m) {
+    if (m->reduce_stream) return ZL_OK;
+    ZL_CHECK_CUDA(cudaStreamCreateWithFlags(&m->reduce_stream, cudaStreamNonBlocking));
+    for (int h = 0; h < 2; ++h)
+        for (cudaEvent_t* e : {&m->ev_o[h], &m->ev_r1[h], &m->ev_dn[h], &m->ev_r2[h]})
+            ZL_CHECK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    return ZL_OK;
+}
+
+static bool prefill_dual_enabled(const zl_llama* m, int n) {
+    // ZL_PREFILL_DUAL: 0 never, 1 always (on one GPU the "reduce" is the residual add: exercises the pipeline),
+    // 2 (default) = when tensor parallel.  Read per call: prefill is not a latency-critical path.
+    const char* e = getenv("ZL_PREFILL_DUAL");
+    const int force = e ? atoi(e) : 2;
+    const auto& c = m->cfg;
+    if (!(c.quant_type == 5 || c.quant_type == 6) || c.fuse < 1 || n < 16) return false;
+    return force == 1 || (force == 2 && c.tp_size > 1);
+}
+
+int prefill_layers_dual(zl_llama* m, const PrefillChunk& pf) {
+    const auto& c = m->cfg;
+    RCHECK(ensure_dual_resources(m));
+    const int D = c.dim_model, d = c.dim_head, dt = c.dtype;
+    const bool tp = c.tp_size > 1;
+    cudaStream_t cs = m->stream, rs = m->reduce_stream;
+    const float scale = 1.0f / sqrtf((float)d);
+    const int n0 = (pf.n / 2 + 7) / 8 * 8 < pf.n ? (pf.n / 2 + 7) / 8 * 8 : pf.n / 2;   // rows of half 0
+    const int r0[2] = {0, n0}, nh[2] = {n0, pf.n - n0};
+    const int len_buf = pf.pos0 + pf.n;
+    auto rows = [&](void* base, int row, size_t row_bytes) { return (char*)base + (size_t)row * row_bytes; };
+    auto reduce = [&](int h) -> int {   // h rows: h += sum over ranks of pend
+        void* hp = rows(m->h, r0[h], (size_t)D * 2);
+        void* pp = rows(m->pend, r0[h], (size_t)D * 2);
+        if (tp) return zl_allreduce_one_shot(m->comm, pp, hp, hp, (size_t)nh[h] * D, dt, c.tp_int8, 0, rs);
+        return zl_element_add_scale(hp, pp, hp, (size_t)nh[h] * D, 1.0f, dt, rs);
+    };
+    for (int l = 0; l < c.num_layers; ++l) {
+        Layer& L = m->layers[l];
+        for (int h = 0; h < 2; ++h) {   // S1
+            if (l > 0) ZL_CHECK_CUDA(cudaStreamWaitEvent(cs, m->ev_r2[h], 0));
+            void* hp = rows(m->h, r0[h], (size_t)D * 2);
+            if (c.fuse >= 2) {
+                RCHECK(w4_gemm(m, hp, D, L.q_qkv, nullptr, nullptr, nh[h], ZL_EPI_QKV_ROPE, L.ln_attn, &L, -1, -1, r0[h], 1));
+            } else {
+                void* qp = rows(m->qkv, r0[h], (size_t)(m->hq + 2 * m->hkv) * d * 2);
+                RCHECK(w4_gemm(m, hp, D, L.q_qkv, nullptr, qp, nh[h], ZL_EPI_NONE, L.ln_attn, nullptr, -1, -1, 0, 1));
+                RCHECK(zl_qkv_rope_append(m->cosb + (size_t)r0[h] * d, m->sinb + (size_t)r0[h] * d, qp,
+                                          rows(m->q, r0[h], (size_t)m->hq * d * 2), m->cur_tb + r0[h], m->d_pos + r0[h],
+                                          L.k_addrs, L.v_addrs, nh[h], m->hq, m->hkv, d, 1, 1, m->d_lens, dt, 0, cs));
+            }
+            // causal rows r0.. of the chunk's mask; keys of BOTH halves are visible as far as the mask allows, so half 1
+            // needs half 0's K/V rows, which the same stream appended just before
+            RCHECK(zl_decode_attention(rows(m->q, r0[h], (size_t)m->hq * d * 2), m->d_lens + pf.task, L.k_addrs + pf.task,
+                                       L.v_addrs + pf.task, m->d_mask + (size_t)r0[h] * len_buf, scale, len_buf,
+                                       rows(m->ao, r0[h], (size_t)m->hq * d * 2), 1, nh[h], m->hq, m->hkv, d, 1, m->attn_ws,
+                                       m->attn_ws_bytes, dt, 0, cs));
+            RCHECK(w4_gemm(m, rows(m->ao, r0[h], (size_t)m->hq * d * 2), m->hq * d, L.q_o, nullptr,
+                           rows(m->pend, r0[h], (size_t)D * 2), nh[h], ZL_EPI_NONE, nullptr, nullptr, -1, -1, 0, 1));
+            ZL_CHECK_CUDA(cudaEventRecord(m->ev_o[h], cs));
+            ZL_CHECK_CUDA(cudaStreamWaitEvent(rs, m->ev_o[h], 0));   // R1
+            RCHECK(reduce(h));
+            ZL_CHECK_CUDA(cudaEventRecord(m->ev_r1[h], rs));
+        }
+        for (int h = 0; h < 2; ++h) {   // S3
+            ZL_CHECK_CUDA(cudaStreamWaitEvent(cs, m->ev_r1[h], 0));
+            void* hp = rows(m->h, r0[h], (size_t)D * 2);
+            void* ap = rows(m->act, r0[h], (size_t)m->ff * 2);
+            RCHECK(w4_gemm(m, hp, D, L.q_gu, nullptr, ap, nh[h], ZL_EPI_SWIGLU, L.ln_ff, nullptr, -1, -1, 0, 1));
+            RCHECK(w4_gemm(m, ap, m->ff, L.q_down, nullptr, rows(m->pend, r0[h], (size_t)D * 2), nh[h], ZL_EPI_NONE, nullptr,
+                           nullptr, -1, -1, 0, 1));
+            ZL_CHECK_CUDA(cudaEventRecord(m->ev_dn[h], cs));
+            ZL_CHECK_CUDA(cudaStreamWaitEvent(rs, m->ev_dn[h], 0));   // R2
+            RCHECK(reduce(h));
+            ZL_CHECK_CUDA(cudaEventRecord(m->ev_r2[h], rs));
+        }
+    }
+    for (int h = 0; h < 2; ++h) ZL_CHECK_CUDA(cudaStreamWaitEvent(cs, m->ev_r2[h], 0));
+    return ZL_OK;
+}
+
 int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* pf = nullptr) {
     const auto& c = m->cfg;
     const int B = pf ? pf->n : n_tasks;   // rows (tokens) of every activation matrix in this launch sequence
@@ -802,7 +901,9 @@ int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* p
     const int mega_stages = (w4 && c.fuse >= 3 && !skip && !pf) ? mega_plan(m, B, len_bucket, &mp) : 0;
     m->mega_used = mega_stages != 0;
     if (mega_stages) ZL_CHECK_CUDA(launch_llama_mega(mp, mega_stages, pdl != 0, st));
-    for (int l = 0; l < (mega_stages ? 0 : c.num_layers); ++l) {
+    const bool dual = pf && prefill_dual_enabled(m, pf->n);
+    if (dual) RCHECK(prefill_layers_dual(m, *pf));
+    for (int l = 0; l < ((mega_stages || dual) ? 0 : c.num_layers); ++l) {
         Layer& L = m->layers[l];
         if (w4) {
             const void* xin = m->xn;
@@ -1003,6 +1104,13 @@ extern "C" void zl_llama_destroy(zl_llama_t* m) {
                     (void*)m->d_pos, (void*)m->d_lens, (void*)m->d_next, (void*)m->d_iota, m->attn_ws, m->argmax_ws, (void*)m->d_mega_layers, (void*)m->d_mega_sync,
                     (void*)m->d_mega_trace, (void*)m->d_tb, (void*)m->d_mask, m->xq, (void*)m->xs})
         if (p) cudaFree(p);
+    if (m->reduce_stream) {
+        cudaStreamSynchronize(m->reduce_stream);
+        for (int h = 0; h < 2; ++h)
+            for (cudaEvent_t e : {m->ev_o[h], m->ev_r1[h], m->ev_dn[h], m->ev_r2[h]})
+                if (e) cudaEventDestroy(e);
+        cudaStreamDestroy(m->reduce_stream);
+    }
     if (m->h_stage) cudaFreeHost(m->h_stage);
     cudaStreamDestroy(m->stream);
     delete m;
