@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import gptq, ops
+from tests.helpers import rel_l2
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -205,3 +206,50 @@ def test_oracle_against_reference_goldens(path):
         pytest.skip("no reference goldens committed yet (parity unpinned)")
     from oracle import check_golden
     check_golden.check_file(path)
+
+
+def test_w8_oracle_functions_are_self_consistent():
+    """INT8 / FP8 Linear restatements (oracle/ops.py): exact integer identities and closeness to the fp Linear."""
+    rng = np.random.default_rng(21)
+    x = ops._t(rng.standard_normal((6, 512)) * 1.3, "f16")
+    w = ops._t(rng.standard_normal((96, 512)) * 0.05, "f16")
+    wq, ws = ops.int8_weight_quant_per_row(w)
+    q, s = ops.int8_quant_per_token(x)
+    assert q.dtype == np.int8 and np.abs(q).max() == 127                    # every token reaches full scale
+    np.testing.assert_allclose(q * s[:, None], x, atol=float(s.max()) * 0.5 + 1e-7)
+    y = ops.int8_linear(x, wq, ops._t(ws, "f16"), "f16")
+    assert rel_l2(y, x @ w.T) < 2e-2
+    # all-zero token: quantises to zeros with scale 0 (device NaN -> int8 conversion), output row is exactly 0
+    x0 = x.copy()
+    x0[2] = 0
+    q0, s0 = ops.int8_quant_per_token(x0)
+    assert not q0[2].any() and s0[2] == 0
+    # layernorm_quant: the int8 twin times its scale reproduces the normalised output
+    ln_w = ops._t(1 + 0.1 * rng.standard_normal(512), "f16")
+    yn, qn, sn = ops.rmsnorm_quant(x, ln_w, 1e-5, 1.0, "f16")
+    np.testing.assert_allclose(qn * sn[:, None], yn, atol=float(sn.max()) * 0.51 + 2e-3)
+    # e4m3: decode(encode) round trip on every finite code, saturation at 448
+    codes = np.arange(256, dtype=np.uint8)
+    vals = ops.e4m3_decode(codes)
+    fin = np.isfinite(vals)
+    np.testing.assert_array_equal(ops.e4m3_round(vals[fin]), vals[fin])
+    assert ops.e4m3_round(np.array([1e6, -1e6], np.float32)).tolist() == [448.0, -448.0]
+    xq, xs = ops.fp8_quant_per_tensor(x, dtype="f16")
+    assert np.abs(xq).max() == 448.0
+    y8 = ops.fp8_linear(x, ops.e4m3_round(w / 0.01), np.float32(0.01), "f16")
+    assert rel_l2(y8, x @ w.T) < 6e-2
+
+
+def test_w8_oracle_model_runs_and_tracks_the_fp_model():
+    from oracle import model as omodel
+    cfg = dict(num_layers=2, dim_model=256, num_heads=4, num_kv_heads=2, dim_head=64, dim_ff=512, vocab_size=512,
+               eps=1e-5, rope_theta=10000.0, rope_llama3=None)
+    sd = omodel.make_state_dict(cfg, 2, 128, False, seed=3)
+    fp = omodel.OracleLlama(cfg, sd, 0, 128, False, "f16")
+    i8 = omodel.OracleLlama(cfg, sd, 2, 128, False, "f16")
+    tok = np.array([7, 300])
+    a, b = fp.decode(tok, [0, 0]), i8.decode(tok, [0, 0])
+    assert np.isfinite(b).all() and rel_l2(b, a) < 5e-2                      # SmoothQuant-level deviation
+    sd8 = omodel.make_state_dict(cfg, 7, 128, False, seed=3)
+    f8 = omodel.OracleLlama(cfg, sd8, 7, 128, False, "f16")
+    assert np.isfinite(f8.decode(tok, [0, 0])).all()
