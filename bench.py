@@ -54,10 +54,39 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.gpu = gpu_index
         self.samples = []
+        self.stamps = []          # host time of every sample
+        self.t_region = None      # mark_region_start(): only samples taken after it describe the timed region
         self.stop_flag = False
         self.proc = None
 
+    def mark_region_start(self):
+        self.t_region = time.time()
+
+    def _run_nvml(self):
+        """5 ms NVML polling (nvidia_ml_py): enough samples inside a ~100 ms timed region.  Any failure falls back to
+        the nvidia-smi loop below."""
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        while not self.stop_flag:
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            r = int(get_reasons(h))
+            flags = ["Active" if r & bits[k] else "Not Active"
+                     for k in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")]
+            self.samples.append([str(self.gpu), str(sm), str(mx), "", ""] + flags)
+            self.stamps.append(time.time())
+            time.sleep(0.005)
+
     def run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -66,6 +95,7 @@ class ClockSampler(threading.Thread):
                 if self.stop_flag:
                     break
                 self.samples.append([x.strip() for x in line.split(",")])
+                self.stamps.append(time.time())
         except Exception:
             pass
 
@@ -74,7 +104,8 @@ class ClockSampler(threading.Thread):
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for s in self.samples:
+        picked = [s for s, ts in zip(self.samples, self.stamps) if self.t_region is None or ts >= self.t_region]
+        for s in (picked or self.samples):   # too short a region for the sampling period: fall back to all samples
             try:
                 sm.append(float(s[1]))
                 mx.append(float(s[2]))
@@ -266,9 +297,10 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.3)
+    time.sleep(0.3)           # lets the nvidia-smi fallback start up; the NVML sampler is already polling
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = dec.lib.zl_launch_count(0)
+    sampler.mark_region_start()
     e0.record(stream)
     for _ in range(args.steps):
         dec.step_device(B)
