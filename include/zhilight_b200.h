@@ -290,7 +290,7 @@ typedef struct zl_llama_config {
     float rope_llama3_factor; /* <= 0: plain rope */
     float rope_low_freq_factor, rope_high_freq_factor, rope_orig_ctx;
     int quant_type; /* model_config.hpp:132-144 QuantType: 0 none, 2 AutoInt8 (fp weights quantised per row at load),
-                     * 5 GPTQ, 6 AWQ, 7 FP8 (e4m3 weights + per-tensor weight_scale) */
+                     * 5 GPTQ, 6 AWQ, 7 FP8 (e4m3 weights + per-tensor weight_scale), 8 GPTQ_Marlin (= 5 with sym) */
     int group_size, sym;
     int dtype; /* ZL_F16 / ZL_BF16 (W4 paths are fp16-only like the reference, q_gemm_k_major.cu:989) */
     int max_batch, max_seq;

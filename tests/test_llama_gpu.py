@@ -241,3 +241,17 @@ def test_dual_stream_prefill_matches_single_stream(lib, cuda, monkeypatch, cfg):
     for p, t in enumerate(prompt[:int(os.environ.get("ZL_TEST_PROMPT", "84"))]):
         ref = orc.decode(np.array([t]), [p])
     assert rel_l2(outs[1][0], ref) <= 5e-3
+
+
+def test_marlin_quant_type_is_served_by_the_gptq_kernels(lib, cuda):
+    """QuantType 8 (GPTQ_Marlin) takes the same symmetric GPTQ checkpoint as QuantType 5 (linear.cpp:1418-1435)."""
+    from zhilight_b200.llama import LlamaDecoder
+    sd = omodel.make_state_dict(TINY, 5, 128, True, seed=17)
+    outs = []
+    for qt, sym in ((5, True), (8, False)):
+        dec = LlamaDecoder(quant_type=qt, sym=sym, max_batch=2, max_seq=32, **TINY)
+        dec.load_state_dict(sd)
+        nxt, logits = dec.decode(np.array([3, 9], np.int32), np.array([0, 0], np.int32), want_logits=True)
+        outs.append(logits.copy())
+        dec.close()
+    np.testing.assert_array_equal(outs[0], outs[1])
