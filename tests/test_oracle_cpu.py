@@ -253,3 +253,33 @@ def test_w8_oracle_model_runs_and_tracks_the_fp_model():
     sd8 = omodel.make_state_dict(cfg, 7, 128, False, seed=3)
     f8 = omodel.OracleLlama(cfg, sd8, 7, 128, False, "f16")
     assert np.isfinite(f8.decode(tok, [0, 0])).all()
+
+
+def test_activation_digit_decomposition_identities():
+    """The integer W4A16 kernel (zhilight_b200/csrc/w4a16_gemm_v3.cu) turns each 128-group of fp16 activations into
+    integers m = round(x * 2^-e) and splits them into two 8-bit digits.  Restated here in numpy: both splittings are
+    exact and the dot product with 4-bit weights reassembles exactly from the per-digit integer dot products."""
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal(128) * rng.choice([1e-3, 1.0, 300.0])).astype(np.float16).astype(np.float32)
+    q = rng.integers(0, 16, size=128).astype(np.int64)
+    for bits, packed in ((14, False), (13, True)):
+        ex = int(np.frexp(np.abs(x).max())[1]) - 1 + 127          # biased exponent of the group maximum
+        e = ex - 127 - bits
+        m = np.rint(x * np.float32(2.0) ** -e).astype(np.int64)
+        assert np.abs(m).max() <= 2 ** (bits + 1)
+        if not packed:      # two IMMAs: signed high byte (floor), unsigned low byte
+            hi, lo = m >> 8, m & 0xFF
+            assert hi.min() >= -128 and hi.max() <= 127 and lo.min() >= 0
+        else:               # one IMMA, both digits signed: lo' = int8(m & 0xff), hi' = (m + 128) >> 8
+            lo = ((m & 0xFF) ^ 0x80) - 0x80
+            hi = (m + 128) >> 8
+            assert hi.min() >= -128 and hi.max() <= 127 and lo.min() >= -128 and lo.max() <= 127
+        np.testing.assert_array_equal(hi * 256 + lo, m)
+        # group dot product with the zero point removed through the exact sum of m (kernel epilogue)
+        z = 8
+        exact = int(((q - z) * m).sum())
+        assert int((q * hi).sum()) * 256 + int((q * lo).sum()) - z * int(m.sum()) == exact
+        # and the value it stands for is within 2^-(bits+1) of the group maximum of the fp32 product
+        ref = float(((q - z) * x.astype(np.float64)).sum())
+        tol = 128 * 15 * float(np.abs(x).max()) * 2.0 ** -(bits + 1)
+        assert abs(exact * 2.0 ** e - ref) <= tol
