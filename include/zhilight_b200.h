@@ -125,8 +125,16 @@ typedef struct zl_w4_fused_args {
     int variant; /* layout of `packed`: 0 ZLW4, 1 ZLW4I (integer kernel; needs the staged activations to fit smem) */
 } zl_w4_fused_args_t;
 int zl_w4a16_gemm_fused(const zl_w4_fused_args_t* args, zl_stream_t stream);
-/* 1 if the exact-integer kernel (variant 1) can run this shape: its staged activations must fit shared memory. */
+/* 1 if the exact-integer kernel (variant 1, M <= 16) can run this shape: its staged activations must fit shared memory. */
 int zl_w4_int_kernel_fits(int M, int N, int K);
+/* which kernel serves (M, N, K) on the ZLW4I layout (variant 1): 3 = exact-integer mma.sync kernel, 4 = tcgen05 / TMEM /
+ * TMA kernel (any M, N % 128 == 0, no fused RMSNorm prologue), 0 = neither (pack variant 0 and use the fp16 mma.sync kernel). */
+int zl_w4_int_layout_route(int M, int N, int K);
+/* last watchdog code published by a tcgen05 kernel on the current device (0 = none); a bounded mbarrier wait that expires
+ * records which pipeline barrier starved and traps instead of hanging the GPU. */
+unsigned zl_w4_tc_watchdog(void);
+/* debug / tests: force the k-split count of the tcgen05 kernel (0 = automatic; also ZL_TC_SPLITS). */
+int zl_w4_tc_set_splits(int splits);
 /* debug: device buffer of grid*16 uint64 globaltimer samples written by the integer kernel (NULL = off). */
 int zl_w4_set_trace(void* buf);
 /* row_map (n_heads_total*dim_head) for zl_w4_pack so that RoPE partners (c, c+d/2) share an MMA tile. */
@@ -297,10 +305,10 @@ typedef struct zl_llama_config {
     int tp_rank, tp_size;
     int use_pdl, use_graph;
     int tp_int8; /* TP all-reduce payload: 0 = activation dtype, 1 = int8 group-32 (REDUCE_TP_INT8 of the reference) */
-    int fuse; /* 0: one kernel per reference operator; 1: RMSNorm folded into the W4 GEMMs; 2: + qkv RoPE/KV-append epilogue;
-               * 3: opt-in persistent whole-model kernel (llama_mega.cu) when the shape fits, else as 2 */
-    int prefill_chunk; /* 0: decode only.  1..32: zl_llama_prefill processes a prompt in chunks of this many tokens
-                        * (chunked prefill, zhilight/config/adapter.py:47-48); W4 models then also keep the ZLW4 layout */
+    int fuse; /* 0: one kernel per reference operator; 1: RMSNorm folded into the W4 GEMMs; 2 (3 is accepted as 2):
+               * + qkv RoPE/KV-append epilogue.  Launches with more than 16 tokens run zl_rmsnorm + the tcgen05 GEMM. */
+    int prefill_chunk; /* 0: decode only.  1..2048: zl_llama_prefill processes a prompt in chunks of this many tokens
+                        * (chunked prefill, zhilight/config/adapter.py:47-48) */
 } zl_llama_config_t;
 
 int zl_llama_create(const zl_llama_config_t* cfg, zl_llama_t** out);
@@ -330,11 +338,11 @@ int zl_llama_sync(zl_llama_t* m);
 /* Chunked prefill of ONE task (SearchTask prompt, src/generator/batch_generator.cpp:1576): appends tokens_host[0..n) at
  * positions pos0.. to the task's KV buffers through the same kernels (M = chunk GEMMs, causal len_q = chunk attention)
  * and returns the greedy next token (and optionally the last position's logits, vocab/tp floats).  Synchronous. */
+/* Prefill keeps its own token / position staging on the device: the (token, position) state of the decode tasks set by
+ * zl_llama_set_state survives a prefill issued between two zl_llama_step_device calls (continuous batching).  It
+ * overwrites the next-token / logits row 0 outputs, which zl_llama_step_device consumes before it returns. */
 int zl_llama_prefill(zl_llama_t* m, int task, const int32_t* tokens_host, int n, int pos0, int32_t* next_token_host,
                      float* logits_host);
-/* debug: (id, globaltimer ns) records of the persistent decode kernel's last launch (ZL_MEGA_TRACE=1 at finalize);
- * out[0] = record count, then pairs. */
-int zl_llama_mega_trace(zl_llama_t* m, unsigned long long* out, int n_words);
 zl_stream_t zl_llama_stream(zl_llama_t* m);
 /* bytes the step must read from HBM per rank (weights + lm_head + norms), kernel launches per step. */
 int zl_llama_stats(zl_llama_t* m, int B, double* weight_bytes, int* kernels_per_step);

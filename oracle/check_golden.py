@@ -122,6 +122,30 @@ def check_w8(g):
             assert _rel(g[key + tag], yo) < (1e-3 if tag == "f16" else 4e-3), (key, tag, _rel(g[key + tag], yo))
 
 
+def check_rope_tables(g):
+    c = gc.case_rope_tables()
+    pos = c["pos"].astype(np.float64)
+    for name, (d, theta, l3) in c["variants"].items():
+        cos, sin = ops.rope_cos_sin(c["pos"], d, theta, l3)
+        # fp32 angles: one ulp of inv_freq (numpy power vs the device's powf) moves the angle by pos * 6e-8 rad
+        atol = (2e-6 + pos * 2.5e-7)[:, None]
+        assert (np.abs(g["cos_" + name] - cos) <= atol).all(), name
+        assert (np.abs(g["sin_" + name] - sin) <= atol).all(), name
+        # position 0 and 1 pin the inverse frequencies themselves (incl. the llama3 wavelength branches)
+        np.testing.assert_allclose(g["sin_" + name][1], sin[1], rtol=3e-6, atol=1e-9)
+
+
+def check_marlin(g):
+    c = gc.case_marlin()
+    qw, qz, sc, _ = gptq.to_k_major(c["qweight"], c["qzeros"], c["scales"], c["g_idx"], 128)
+    w = gptq.dequant_k_major_f32(qw, qz, sc, True)                  # zero fixed at 8 (u4b8)
+    for m, x in c["xs"].items():
+        assert _rel(g["y%d" % m], gptq.gemm_f32(x, w)) < 1e-3, m
+    # gptq_marlin_repack only permutes nibbles
+    nib = lambda a: np.sort(np.stack([(a.view(np.uint32) >> np.uint32(4 * i)) & np.uint32(15) for i in range(8)]).reshape(-1))
+    np.testing.assert_array_equal(nib(g["repacked"]), nib(np.ascontiguousarray(c["qweight"])))
+
+
 CHECKS = {
     "ref_gptq_layout": lambda g: check_layout(g, False),
     "ref_awq_layout": lambda g: check_layout(g, True),
@@ -134,6 +158,8 @@ CHECKS = {
     "ref_attention_long": lambda g: check_attention(g, True),
     "ref_int8": check_int8,
     "ref_w8": check_w8,
+    "ref_rope_tables": check_rope_tables,
+    "ref_marlin": check_marlin,
 }
 
 

@@ -40,6 +40,42 @@ class Ref:
     def p(t):
         return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
+    # ---- rope tables, Marlin, native AWQ (round 2) ----
+    def rope_cos_sin(self, pos, d, theta, llama3=None):
+        t = pos.numel()
+        cos = torch.empty((t, d), dtype=torch.float32, device=self.dev)
+        sin = torch.empty_like(cos)
+        l3 = llama3 or {}
+        self._chk(self.lib.zlref_rope_cos_sin(self.p(pos), t, d, ctypes.c_float(theta), int(llama3 is not None),
+                                              ctypes.c_float(l3.get("factor", 1.0)), ctypes.c_float(l3.get("low", 1.0)),
+                                              ctypes.c_float(l3.get("high", 4.0)), int(l3.get("orig", 8192)),
+                                              self.p(cos), self.p(sin)))
+        return cos, sin
+
+    def marlin_repack(self, qweight_hf):
+        k8, n = qweight_hf.shape
+        out = torch.empty((k8 * 8 // 16, 2 * n), dtype=torch.int32, device=self.dev)
+        self._chk(self.lib.zlref_marlin_repack(self.p(qweight_hf), n, k8 * 8, self.p(out)))
+        return out
+
+    def marlin_gemm(self, x, qweight_hf, scales_hf):
+        """x (M, K) f16; HF GPTQ qweight (K/8, N) int32 (symmetric, u4b8), scales (K/g, N) f16 -> (M, N) f16."""
+        m, k = x.shape
+        n = qweight_hf.shape[1]
+        out = torch.empty((m, n), dtype=torch.float16, device=self.dev)
+        self._chk(self.lib.zlref_marlin_gemm(self.p(x), self.p(qweight_hf), self.p(scales_hf), m, n, k, scales_hf.shape[0],
+                                             self.p(out)))
+        return out
+
+    def awq_gemm(self, x, qweight, scales, qzeros):
+        """native awq_gemm (split-k 32): qweight (K, N/8) int32, scales (K/g, N) f16, qzeros (K/g, N/8) int32."""
+        m, k = x.shape
+        n = scales.shape[1]
+        out = torch.empty((m, n), dtype=torch.float16, device=self.dev)
+        self._chk(self.lib.zlref_awq_gemm(self.p(x), self.p(qweight), self.p(scales), self.p(qzeros), m, n, k, scales.shape[0],
+                                          self.p(out)))
+        return out
+
     # ---- layout ----
     def gptq_to_k_major(self, qweight, qzeros, scales, awq=False):
         lib, p = self.lib, self.p
@@ -306,6 +342,19 @@ def main(out_dir, lib_path=None):
         outs["f8_y_" + tag] = n(ref.fp8_gemm(fq, fs, ref.t(c["w_f8"]), sw8, None, dt).float())
         outs["f8_y_bias_" + tag] = n(ref.fp8_gemm(fq, fs, ref.t(c["w_f8"]), sw8, ref.t(c["bias"]).to(dt), dt).float())
     np.savez(os.path.join(out_dir, "ref_w8.npz"), **outs)
+
+    c = gc.case_rope_tables()
+    outs = {}
+    for name, (d, theta, l3) in c["variants"].items():
+        cos, sin = ref.rope_cos_sin(ref.t(c["pos"]), d, theta, l3)
+        outs["cos_" + name], outs["sin_" + name] = n(cos), n(sin)
+    np.savez(os.path.join(out_dir, "ref_rope_tables.npz"), **outs)
+
+    c = gc.case_marlin()
+    outs = {"repacked": n(ref.marlin_repack(ref.t(c["qweight"])))}
+    for m, x in c["xs"].items():
+        outs["y%d" % m] = n(ref.marlin_gemm(ref.t(x), ref.t(c["qweight"]), ref.t(c["scales"])))
+    np.savez(os.path.join(out_dir, "ref_marlin.npz"), **outs)
     print("wrote goldens to", out_dir)
 
 

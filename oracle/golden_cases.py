@@ -104,3 +104,25 @@ def case_w8():
     w_f8 = r.integers(0, 256, size=(n, k)).astype(np.uint8)
     w_f8[(w_f8 & 0x7F) == 0x7F] = 0x38                         # no NaN encodings (0x7f / 0xff)
     return dict(x=x, ln_w=ln_w, eps=1e-5, w_q=w_q, w_s=w_s, bias=bias, w_f8=w_f8, w_f8_scale=np.float32(0.0123))
+
+
+ROPE_TABLE_VARIANTS = {
+    "plain_d64": (64, 10000.0, None),
+    "plain_d128": (128, 10000.0, None),
+    "l3f8_d128": (128, 500000.0, dict(factor=8.0, low=1.0, high=4.0, orig=8192.0)),
+    "l3f32_d64": (64, 500000.0, dict(factor=32.0, low=1.0, high=4.0, orig=8192.0)),
+}
+
+
+def case_rope_tables():
+    """RopePreparer inputs (rope_preparer.cu:49-161): plain and llama3 (factor 8: Llama-3.1, factor 32: Llama-3.2)."""
+    return dict(pos=np.array([0, 1, 2, 63, 4095, 8191, 8192, 100000], dtype=np.int32), variants=ROPE_TABLE_VARIANTS)
+
+
+def case_marlin():
+    """QuantType 8: symmetric (u4b8) g128 HF-GPTQ checkpoint as GPTQMarlin loads it (linear.cpp:1402-1435)."""
+    k, n, g = 512, 256, 128
+    qw, qz, sc, gi = gptq.make_gptq_checkpoint(k, n, g, True, seed=131)
+    r = _rng(132)
+    xs = {m: r.standard_normal((m, k)).astype(np.float16) for m in (1, 5, 17)}
+    return dict(qweight=qw, qzeros=qz, scales=sc, g_idx=gi, xs=xs, K=k, N=n, G=k // g)

@@ -179,3 +179,81 @@ def test_fp8_linear_vs_reference(lib, ref, cuda, dt):
     y_ref = ref.fp8_gemm(rq, rs, w8, sw, None, dt).float().cpu().numpy()
     y = ops.w8a8_gemm(q, s, w8, sw, dt, kind=ops.W8_FP8).float().cpu().numpy()
     assert rel_l2(y, y_ref) < (1e-3 if dt == torch.float16 else 4e-3)
+
+
+# ---- round 2: rope tables, Marlin, native AWQ against the reference's own kernels ----
+LLAMA3_8 = dict(factor=8.0, low=1.0, high=4.0, orig=8192)
+LLAMA3_32 = dict(factor=32.0, low=1.0, high=4.0, orig=8192)
+
+
+@pytest.mark.parametrize("d", [64, 128])
+@pytest.mark.parametrize("theta,l3", [(10000.0, None), (500000.0, LLAMA3_8), (500000.0, LLAMA3_32)],
+                         ids=["plain", "llama3-f8", "llama3-f32"])
+def test_rope_cos_sin_vs_reference_rope_preparer(lib, ref, cuda, d, theta, l3):
+    """zl_rope_cos_sin against RopePreparer / KERNEL_rope_cos_sin(_llama3) (src/nn/position/rope_preparer.cu:49-161).
+    Both evaluate the same fp32 expression, so the tables agree to the last bits even at position 100000 where a
+    1-ulp change of inv_freq already moves cos by 1e-2: every llama3-rope model depends on this table."""
+    from zhilight_b200 import ops
+    pos = torch.tensor([0, 1, 2, 63, 4095, 8191, 8192, 100000], dtype=torch.int32, device=cuda)
+    c_ref, s_ref = ref.rope_cos_sin(pos, d, theta, l3)
+    c, s = ops.rope_cos_sin(pos, d, theta, l3)
+    torch.testing.assert_close(c, c_ref, rtol=0, atol=2e-6)
+    torch.testing.assert_close(s, s_ref, rtol=0, atol=2e-6)
+    assert float((c == c_ref).float().mean()) > 0.99 and float((s == s_ref).float().mean()) > 0.99
+
+
+def _sym_checkpoint(k, n, seed):
+    rng = np.random.default_rng(seed)
+    qw = rng.integers(0, 2 ** 32, size=(k // 8, n), dtype=np.uint64).astype(np.uint32).view(np.int32)
+    sc = (0.002 + 0.004 * rng.random((k // 128, n))).astype(np.float16)
+    qz = np.full((k // 128, n // 8), 0x77777777, dtype=np.uint32).view(np.int32)      # stored 7 -> zero 8 (u4b8)
+    return qw, qz, sc
+
+
+@pytest.mark.parametrize("m", [1, 16, 32, 64])
+@pytest.mark.parametrize("k,n", [(4096, 4096), (4096, 14336)])
+def test_quant_type_8_vs_reference_marlin_kernel(lib, ref, cuda, k, n, m):
+    """QuantType 8 (GPTQ_Marlin): our kernels on a symmetric g128 checkpoint against the reference's gptq_marlin_gemm
+    (src/nn/quant/marlin/gptq_marlin.cu:2034-2192) fed by gptq_marlin_repack + the scale permutation of
+    GPTQMarlin::post_load (linear.cpp:1402-1428).  Marlin multiplies fp16 dequantised weights with fp32 accumulation;
+    M <= 16 runs our exact-integer kernel, M > 16 the tcgen05 kernel: both within 1e-3 (L2) of it and of the fp32 oracle."""
+    from zhilight_b200 import ops
+    qw, qz, sc = _sym_checkpoint(k, n, 5)
+    x = torch.randn(m, k, generator=torch.Generator().manual_seed(m)).half().to(cuda)
+    y_ref = ref.marlin_gemm(x, ref.t(qw), ref.t(sc)).float().cpu().numpy()
+    o_qw, o_qz, o_sc = ops.gptq_to_k_major(ref.t(qw), ref.t(qz), ref.t(sc))
+    packed = ops.w4_pack(o_qw, o_qz, o_sc, 128, True, variant=1)
+    y = ops.w4a16_gemm_fused(x, packed, n, k, variant=1).float().cpu().numpy()
+    k_qw, k_qz, k_sc, _ = gptq.to_k_major(qw, qz, sc, np.arange(k) // 128, 128)
+    exact = gptq.gemm_f32(x.cpu().numpy(), gptq.dequant_k_major_f32(k_qw, k_qz, k_sc, True))
+    assert rel_l2(y, y_ref) <= 1e-3
+    assert rel_l2(y, exact) <= 1e-3 and rel_l2(y_ref, exact) <= 1e-3
+
+
+def test_marlin_repack_is_a_permutation_of_the_checkpoint(lib, ref, cuda):
+    """gptq_marlin_repack (gptq_marlin_repack.cu:258-318) only permutes nibbles: same multiset per 16 x 64 tile."""
+    k, n = 256, 128
+    qw, _, _ = _sym_checkpoint(k, n, 9)
+    r = ref.marlin_repack(ref.t(qw)).cpu().numpy().view(np.uint32)
+    assert r.shape == (k // 16, 2 * n)
+    nib = lambda a: np.sort(np.stack([(a >> (4 * i)) & 15 for i in range(8)]).reshape(-1))
+    np.testing.assert_array_equal(nib(r), nib(qw.view(np.uint32)))
+
+
+@pytest.mark.parametrize("m", [1, 8, 32])
+def test_awq_native_gemm_vs_ours(lib, ref, cuda, m):
+    """QuantType 6 through the reference's native awq_gemm (src/nn/quant/awq/gemm_kernels.cu:404-468, split-k 32) against
+    our AWQ path (shuffle_awq / un_shuffle into the k-major layout, then the W4A16 kernels): same w = (q - z) * s."""
+    from zhilight_b200 import ops
+    k, n, g = 2048, 1024, 128
+    rng = np.random.default_rng(3)
+    qw = rng.integers(0, 2 ** 32, size=(k, n // 8), dtype=np.uint64).astype(np.uint32).view(np.int32)
+    qz = rng.integers(0, 2 ** 32, size=(k // g, n // 8), dtype=np.uint64).astype(np.uint32).view(np.int32)
+    sc = (0.002 + 0.004 * rng.random((k // g, n))).astype(np.float16)
+    x = torch.randn(m, k, generator=torch.Generator().manual_seed(7)).half().to(cuda)
+    y_ref = ref.awq_gemm(x, ref.t(qw), ref.t(sc), ref.t(qz)).float().cpu().numpy()
+    o_qw, o_qz, o_sc = ops.gptq_to_k_major(ref.t(qw), ref.t(qz), ref.t(sc), is_awq=True)
+    packed = ops.w4_pack(o_qw, o_qz, o_sc, 128, False, variant=1)
+    y = ops.w4a16_gemm_fused(x, packed, n, k, variant=1).float().cpu().numpy()
+    # awq_gemm sums 32 fp16 partial tensors (KERNEL_sum_dim0): it is the noisier side
+    assert rel_l2(y, y_ref) <= 3e-3

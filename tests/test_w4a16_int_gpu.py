@@ -93,6 +93,39 @@ def test_edge_activations_int(lib, cuda):
         assert rel_l2(y[i][f], ref[i][f]) <= 2e-3, i
 
 
+@pytest.mark.parametrize("m", [2, 6, 12])
+def test_nonfinite_activations_propagate_int(lib, cuda, m):
+    """Inf / NaN in the activations: the reference GEMV (q_gemm_k_major.cu:127-173) multiplies them through and every
+    output of that token becomes NaN or +-Inf.  The integer decomposition cannot carry them, so the kernel poisons the
+    token's outputs with NaN -- the non-finite pattern must equal the fp32 oracle's, and other tokens stay exact."""
+    from zhilight_b200 import ops
+    k, n = 512, 96
+    w, packed_i, _, _ = _setup(cuda, k, n, False, 11)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(m, k, generator=g).half()
+    x[0, 7] = float("inf")
+    x[1, 300] = float("nan")
+    if m > 2:
+        x[2, 130] = float("-inf")
+        x[2, 131] = float("inf")
+    y = ops.w4a16_gemm_fused(x.to(cuda), packed_i, n, k, variant=1).float().cpu().numpy()
+    with np.errstate(invalid="ignore", over="ignore"):
+        ref = gptq.gemm_f32(x.numpy(), w)
+    bad_rows = [0, 1] + ([2] if m > 2 else [])
+    for i in range(m):
+        if i in bad_rows:
+            assert not np.isfinite(ref[i]).any(), i           # oracle: Inf * w is +-Inf (NaN where w == 0), NaN stays NaN
+            assert not np.isfinite(y[i]).any(), i             # ours: the whole token is poisoned
+        else:
+            assert np.isfinite(y[i]).all()
+            assert rel_l2(y[i], ref[i]) <= TOL
+    # fused RMSNorm prologue: Inf * rsqrt(Inf) is NaN in the reference's layernorm too (layernorm.cu:9-42)
+    lw = torch.ones(k).half()
+    y2 = ops.w4a16_gemm_fused(x.to(cuda), packed_i, n, k, variant=1, ln_weight=lw.to(cuda)).float().cpu().numpy()
+    for i in bad_rows:
+        assert not np.isfinite(y2[i]).any(), i
+
+
 @pytest.mark.parametrize("m", [1, 3])
 def test_epilogues_and_fused_norm_int(lib, cuda, m):
     from zhilight_b200 import ops

@@ -57,7 +57,7 @@ class W4FusedArgs(ctypes.Structure):
 _SCALARS = {
     "int": ctypes.c_int, "float": ctypes.c_float, "double": ctypes.c_double, "size_t": ctypes.c_size_t,
     "uint64_t": ctypes.c_uint64, "uint32_t": ctypes.c_uint32, "int32_t": ctypes.c_int32,
-    "long long": ctypes.c_longlong, "zl_stream_t": ctypes.c_void_p, "void": None,
+    "long long": ctypes.c_longlong, "zl_stream_t": ctypes.c_void_p, "void": None, "unsigned": ctypes.c_uint,
 }
 
 

@@ -43,6 +43,20 @@ constexpr int kWarp = 32;
 
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// SM count of the CURRENT device, cached per device id (one process may drive several devices: one host thread per
+// GPU in the reference engine, engine.cpp:115-117).  A benign race only repeats the query.
+inline int device_sm_count() {
+    static int cache[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    if (dev >= 0 && dev < 64) cache[dev] = n;
+    return n;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Programmatic dependent launch (PDL).  Every kernel in the decode chain calls pdl_trigger() as
 // early as possible (its dependents only prefetch read-only weights before their own pdl_wait())

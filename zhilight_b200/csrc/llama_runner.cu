@@ -7,7 +7,6 @@
 // layer with no graph; here a layer is 8 launches chained with programmatic dependent launch inside one
 // CUDA graph per batch size.
 #include "common.cuh"
-#include "mega_params.h"
 #include "w4_layout.cuh"
 
 #include <cstdlib>
@@ -76,6 +75,18 @@ struct zl_llama {
     size_t attn_ws_bytes = 0;
     void* argmax_ws = nullptr;
     int32_t* h_stage = nullptr;   // pinned: tokens | pos | lens | next
+    // zl_llama_set_state staging: pinned H2D copies read the host buffer when they EXECUTE, so a set_state -> step_device
+    // loop that runs ahead of the GPU must not rewrite a slot whose copy is still queued: ring of slots, one event each
+    static constexpr int kStageSlots = 8;
+    int32_t* h_ring = nullptr;    // pinned [kStageSlots][2 * max_batch]
+    cudaEvent_t ring_ev[kStageSlots] = {};
+    bool ring_used[kStageSlots] = {};
+    int ring_next = 0;
+    // prefill keeps its own (token, position) arrays: the decode-state arrays d_tokens / d_pos of tasks 0..B-1 survive a
+    // prefill that happens between two zl_llama_step_device calls (continuous batching)
+    int32_t *d_pf_tokens = nullptr, *d_pf_pos = nullptr;
+    const int32_t* cur_pos = nullptr;      // positions of the launch sequence being enqueued (d_pos or d_pf_pos)
+    const int32_t* cur_tokens = nullptr;
     zl_comm_t* comm = nullptr;            // TP exchange (set by zl_llama_set_comm when tp_size > 1)
     int vshard = 0;                       // vocabulary rows of lm_head held by this rank
     void* cand = nullptr;                 // [B] {float value, int index} local argmax candidates
@@ -84,11 +95,6 @@ struct zl_llama {
     int cur_max_len = 0;                            // host-side upper bound of buf_lens (positions + 1)
     double weight_bytes = 0;
     int kernels_per_step = 0;
-    // persistent whole-model kernel (cfg.fuse >= 3): per-layer descriptors, grid-barrier words, debug trace
-    zl::MegaLayer* d_mega_layers = nullptr;
-    unsigned* d_mega_sync = nullptr;        // [0] barrier counter (zeroed every step), [1] sticky abort flag
-    unsigned long long* d_mega_trace = nullptr;
-    bool mega_used = false;
     // chunked prefill (cfg.prefill_chunk > 0): activation buffers hold tok_cap = max(max_batch, chunk) tokens
     int tok_cap = 0;
     // dual-stream chunked prefill (EncoderLayer::dual_stream_encode, block.cpp:205-441): compute stream = m->stream
@@ -199,6 +205,44 @@ void drop(zl_llama* m, const std::string& name) {
     }
 }
 
+// frees device temporaries on every exit path of a load helper
+struct DevTmp {
+    std::vector<void*> ptrs;
+    ~DevTmp() {
+        for (void* p : ptrs)
+            if (p) cudaFree(p);
+    }
+    int alloc(void** p, size_t bytes) {
+        int rc = dmalloc(p, bytes);
+        if (rc == ZL_OK) ptrs.push_back(*p);
+        return rc;
+    }
+};
+
+int fail_state(int line, const std::string& msg, int code = ZL_ERR_STATE) {
+    zl_set_last_error(__FILE__, line, msg.c_str());
+    return code;
+}
+
+// g_idx of a desc_act / act-order checkpoint is not k / group_size; the reference then gathers rows by argsort(g_idx)
+// and permutes the activations at run time (linear.cpp:1092-1094, 1145-1146, 1168-1210).  The fused kernels here have no
+// run-time activation permute, so such a checkpoint is rejected at load instead of producing garbage.
+int check_g_idx_sequential(zl_llama* m, const std::string& prefix, int K) {
+    const Staged* gi = find(m, prefix + ".g_idx");
+    if (!gi) return ZL_OK;
+    if ((size_t)gi->rows * gi->cols != (size_t)K || gi->elem != 4)
+        return fail_state(__LINE__, "ill-shaped g_idx for " + prefix + " (expected K int32)");
+    std::vector<int32_t> host(K);
+    ZL_CHECK_CUDA(cudaMemcpyAsync(host.data(), gi->ptr, (size_t)K * 4, cudaMemcpyDeviceToHost, m->stream));
+    ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+    for (int k = 0; k < K; ++k)
+        if (host[k] != k / m->cfg.group_size)
+            return fail_state(__LINE__, "act-order (desc_act) GPTQ checkpoint: " + prefix +
+                                            ".g_idx is not sequential; not supported by the fused W4 kernels",
+                              ZL_ERR_UNSUPPORTED);
+    return ZL_OK;
+}
+
 // HF GPTQ/AWQ tensors of one Linear -> reference k-major tensors written at row offset n_off of the fused
 // k-major buffers (linear.cpp:1139-1160 preprocess_weight + 1085-1099 transpose_weight).
 int to_k_major(zl_llama* m, const std::string& prefix, int K, int N, uint32_t* qw_km, uint8_t* qz_km, __half* sc_km,
@@ -206,36 +250,37 @@ int to_k_major(zl_llama* m, const std::string& prefix, int K, int N, uint32_t* q
     const Staged* qw = find(m, prefix + ".qweight");
     const Staged* qz = find(m, prefix + ".qzeros");
     const Staged* sc = find(m, prefix + ".scales");
-    if (!qw || !qz || !sc) {
-        zl_set_last_error(__FILE__, __LINE__, ("missing GPTQ tensors for " + prefix).c_str());
-        return ZL_ERR_STATE;
-    }
+    if (!qw || !qz || !sc) return fail_state(__LINE__, "missing GPTQ tensors for " + prefix);
     const int G = K / m->cfg.group_size;
     const bool awq = m->cfg.quant_type == 6;
+    // every shape / element size is validated BEFORE the first kernel touches the tensors (in-place transforms below)
+    const bool qw_ok = awq ? (qw->rows == K && qw->cols == N / 8) : (qw->rows == K / 8 && qw->cols == N);
+    if (!qw_ok || qw->elem != 4) return fail_state(__LINE__, "ill-shaped qweight for " + prefix, ZL_ERR_INVALID_ARG);
+    if (qz->rows != G || qz->cols != N / 8 || qz->elem != 4)
+        return fail_state(__LINE__, "ill-shaped qzeros for " + prefix + " (expected (K/g, N/8) int32)", ZL_ERR_INVALID_ARG);
+    if (sc->rows != G || sc->cols != N || sc->elem != 2)
+        return fail_state(__LINE__, "ill-shaped scales for " + prefix + " (expected (K/g, N) fp16)", ZL_ERR_INVALID_ARG);
+    RCHECK(check_g_idx_sequential(m, prefix, K));
     cudaStream_t st = m->stream;
+    DevTmp tmp;
     uint32_t* w_kn = nullptr;   // (K/8, N)
     if (awq) {
-        ZL_CHECK_ARG(qw->rows == K && qw->cols == N / 8);
-        RCHECK(dmalloc((void**)&w_kn, (size_t)(K / 8) * N * 4));
+        RCHECK(tmp.alloc((void**)&w_kn, (size_t)(K / 8) * N * 4));
         RCHECK(zl_awq_shuffle((const uint32_t*)qw->ptr, w_kn, K, N, 1, st));
         RCHECK(zl_awq_un_shuffle((uint32_t*)qz->ptr, G, N / 8, st));
     } else {
-        ZL_CHECK_ARG(qw->rows == K / 8 && qw->cols == N);
         w_kn = (uint32_t*)qw->ptr;
         RCHECK(zl_gptq_shuffle(w_kn, nullptr, nullptr, K, N, st));
         RCHECK(zl_gptq_increase_zero((uint32_t*)qz->ptr, (size_t)G * (N / 8), st));
     }
-    ZL_CHECK_ARG(qz->rows == G && qz->cols == N / 8 && sc->rows == G && sc->cols == N);
     uint8_t* z8 = nullptr;   // (G, N)
-    RCHECK(dmalloc((void**)&z8, (size_t)G * N));
+    RCHECK(tmp.alloc((void**)&z8, (size_t)G * N));
     RCHECK(zl_q4_to_q8((const uint32_t*)qz->ptr, z8, (size_t)G * (N / 8), st));
     // transposes straight into the fused buffers (row offset n_off)
     RCHECK(zl_transpose_2d(w_kn, qw_km + (size_t)n_off * (K / 8), K / 8, N, 4, st));
     RCHECK(zl_transpose_2d(z8, qz_km + (size_t)n_off * G, G, N, 1, st));
     RCHECK(zl_transpose_2d(sc->ptr, sc_km + (size_t)n_off * G, G, N, 2, st));
     ZL_CHECK_CUDA(cudaStreamSynchronize(st));
-    cudaFree(z8);
-    if (awq) cudaFree(w_kn);
     (void)n_total;
     return ZL_OK;
 }
@@ -248,9 +293,10 @@ int build_w4(zl_llama* m, const std::vector<std::string>& prefixes, const std::v
     uint32_t* qw_km = nullptr;
     uint8_t* qz_km = nullptr;
     __half* sc_km = nullptr;
-    RCHECK(dmalloc((void**)&qw_km, (size_t)N * (K / 8) * 4));
-    RCHECK(dmalloc((void**)&qz_km, (size_t)N * G));
-    RCHECK(dmalloc((void**)&sc_km, (size_t)N * G * 2));
+    DevTmp tmp;   // released on every exit path
+    RCHECK(tmp.alloc((void**)&qw_km, (size_t)N * (K / 8) * 4));
+    RCHECK(tmp.alloc((void**)&qz_km, (size_t)N * G));
+    RCHECK(tmp.alloc((void**)&sc_km, (size_t)N * G * 2));
     int off = 0;
     bool any_bias = false;
     for (size_t i = 0; i < prefixes.size(); ++i) {
@@ -260,19 +306,21 @@ int build_w4(zl_llama* m, const std::vector<std::string>& prefixes, const std::v
     }
     int32_t* row_map = nullptr;
     if (swiglu) {
-        RCHECK(dmalloc((void**)&row_map, (size_t)N * 4));
+        RCHECK(tmp.alloc((void**)&row_map, (size_t)N * 4));
         k_swiglu_row_map<<<cdiv(N, 256), 256, 0, m->stream>>>(row_map, N / 2);
         ZL_CHECK_LAUNCH();
     } else if (qkv_rope) {
-        RCHECK(dmalloc((void**)&row_map, (size_t)N * 4));
+        RCHECK(tmp.alloc((void**)&row_map, (size_t)N * 4));
         RCHECK(zl_qkv_rope_row_map(row_map, N / m->cfg.dim_head, m->cfg.dim_head, m->stream));
     }
     const size_t pbytes = zl_w4_packed_bytes(N, K, m->cfg.group_size);
     ZL_CHECK_SUPPORTED(pbytes > 0);
-    // the integer kernel serves every batch size whose staged activations fit shared memory; the fp16-MMA
-    // layout is only materialised when the configured max_batch needs it
+    // the ZLW4I layout serves the exact-integer kernel (M <= 16 when its staged activations fit) and the tcgen05 kernel
+    // (any M, N % 128 == 0); the fp16 mma.sync layout is only materialised when some launch size has neither
     const int m_max = m->cfg.prefill_chunk > m->cfg.max_batch ? m->cfg.prefill_chunk : m->cfg.max_batch;
-    const bool need_half = !zl_w4_int_kernel_fits(m_max, N, K) || getenv("ZL_W4_FORCE_HALF");
+    bool need_half = getenv("ZL_W4_FORCE_HALF") != nullptr;
+    for (int mm = 1; mm <= (m_max < 17 ? m_max : 17); ++mm)
+        if (!zl_w4_int_layout_route(mm, N, K)) need_half = true;
     RCHECK(dmalloc(&out->packed_i, pbytes));
     RCHECK(zl_w4_pack_v(qw_km, qz_km, sc_km, row_map, out->packed_i, N, K, m->cfg.group_size, m->cfg.sym, 1,
                         m->stream));
@@ -287,9 +335,12 @@ int build_w4(zl_llama* m, const std::vector<std::string>& prefixes, const std::v
         off = 0;
         for (size_t i = 0; i < prefixes.size(); ++i) {
             const Staged* b = find(m, prefixes[i] + ".bias");
-            if (b)
+            if (b) {
+                if ((size_t)b->rows * b->cols != (size_t)ns[i] || b->elem != 2)
+                    return fail_state(__LINE__, "ill-shaped bias for " + prefixes[i], ZL_ERR_INVALID_ARG);
                 ZL_CHECK_CUDA(cudaMemcpyAsync((char*)out->bias + (size_t)off * 2, b->ptr, (size_t)ns[i] * 2,
                                               cudaMemcpyDeviceToDevice, m->stream));
+            }
             off += ns[i];
         }
         if (row_map) {   // the fused epilogues index bias by packed row
@@ -302,10 +353,6 @@ int build_w4(zl_llama* m, const std::vector<std::string>& prefixes, const std::v
         }
     }
     ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
-    cudaFree(qw_km);
-    cudaFree(qz_km);
-    cudaFree(sc_km);
-    if (row_map) cudaFree(row_map);
     for (auto& p : prefixes) {
         drop(m, p + ".qweight");
         drop(m, p + ".qzeros");
@@ -328,7 +375,7 @@ int build_dense(zl_llama* m, const std::vector<std::string>& prefixes, const std
     bool any_bias = false;
     for (size_t i = 0; i < prefixes.size(); ++i) {
         const Staged* w = find(m, prefixes[i] + ".weight");
-        if (!w || w->rows != ns[i] || w->cols != K) {
+        if (!w || w->rows != ns[i] || w->cols != K || w->elem != 2) {
             zl_set_last_error(__FILE__, __LINE__, ("missing/ill-shaped dense weight " + prefixes[i]).c_str());
             return ZL_ERR_STATE;
         }
@@ -434,7 +481,7 @@ int build_fp8(zl_llama* m, const std::vector<std::string>& prefixes, const std::
 
 int take_vector(zl_llama* m, const std::string& name, int n, void** out) {
     auto it = m->staged.find(name);
-    if (it == m->staged.end() || (size_t)it->second.rows * it->second.cols != (size_t)n) {
+    if (it == m->staged.end() || (size_t)it->second.rows * it->second.cols != (size_t)n || it->second.elem != 2) {
         zl_set_last_error(__FILE__, __LINE__, ("missing/ill-shaped tensor " + name).c_str());
         return ZL_ERR_STATE;
     }
@@ -505,8 +552,8 @@ int alloc_runtime(zl_llama* m) {
         ZL_CHECK_CUDA(cudaMemsetAsync(L.vbuf, 0, kv_task * B, m->stream));
         RCHECK(dmalloc((void**)&L.k_addrs, sizeof(void*) * B));
         RCHECK(dmalloc((void**)&L.v_addrs, sizeof(void*) * B));
-        k_ptr_table<<<1, 256, 0, m->stream>>>(L.k_addrs, (char*)L.kbuf, kv_task, B);
-        k_ptr_table<<<1, 256, 0, m->stream>>>(L.v_addrs, (char*)L.vbuf, kv_task, B);
+        k_ptr_table<<<cdiv(B, 256), 256, 0, m->stream>>>(L.k_addrs, (char*)L.kbuf, kv_task, B);
+        k_ptr_table<<<cdiv(B, 256), 256, 0, m->stream>>>(L.v_addrs, (char*)L.vbuf, kv_task, B);
         ZL_CHECK_LAUNCH();
     }
     const int T = c.prefill_chunk > B ? c.prefill_chunk : B;   // tokens per launch: decode batch or prefill chunk
@@ -524,8 +571,8 @@ int alloc_runtime(zl_llama* m) {
     RCHECK(dmalloc(&m->cand_all, (size_t)((B * 8 + 15) / 16) * 16 * c.tp_size));
     RCHECK(dmalloc((void**)&m->cosb, (size_t)T * d * 4));
     RCHECK(dmalloc((void**)&m->sinb, (size_t)T * d * 4));
-    RCHECK(dmalloc((void**)&m->d_tokens, T * 4));
-    RCHECK(dmalloc((void**)&m->d_pos, T * 4));
+    RCHECK(dmalloc((void**)&m->d_tokens, B * 4));
+    RCHECK(dmalloc((void**)&m->d_pos, B * 4));
     RCHECK(dmalloc((void**)&m->d_lens, B * 4));
     if (c.quant_type == 2 || c.quant_type == 7) {
         int kmax = D > m->ff ? D : m->ff;
@@ -535,16 +582,21 @@ int alloc_runtime(zl_llama* m) {
     }
     if (c.prefill_chunk > 0) {
         RCHECK(dmalloc((void**)&m->d_tb, T * 4));
+        RCHECK(dmalloc((void**)&m->d_pf_tokens, T * 4));
+        RCHECK(dmalloc((void**)&m->d_pf_pos, T * 4));
         RCHECK(dmalloc((void**)&m->d_mask, (size_t)c.prefill_chunk * c.max_seq));
     }
     RCHECK(dmalloc((void**)&m->d_next, B * 4));
     RCHECK(dmalloc((void**)&m->d_iota, B * 4));
-    k_iota<<<1, 256, 0, m->stream>>>(m->d_iota, B);
+    k_iota<<<cdiv(B, 256), 256, 0, m->stream>>>(m->d_iota, B);
     ZL_CHECK_LAUNCH();
     m->attn_ws_bytes = zl_decode_attention_workspace_bytes(T, 1, m->hq, d, c.max_seq);
     RCHECK(dmalloc(&m->attn_ws, m->attn_ws_bytes));
     RCHECK(dmalloc(&m->argmax_ws, zl_argmax_workspace_bytes(B)));
     ZL_CHECK_CUDA(cudaMallocHost((void**)&m->h_stage, sizeof(int32_t) * (4 * B + 4 + T)));
+    ZL_CHECK_CUDA(cudaMallocHost((void**)&m->h_ring, sizeof(int32_t) * zl_llama::kStageSlots * 2 * B));
+    for (int i = 0; i < zl_llama::kStageSlots; ++i)
+        ZL_CHECK_CUDA(cudaEventCreateWithFlags(&m->ring_ev[i], cudaEventDisableTiming));
     ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
     return ZL_OK;
 }
@@ -587,7 +639,7 @@ static void prefetch_target(zl_llama* m, int l, int slot, int B, const void** pt
     else if (what == 3) t = &L.q_down;
     else if (what == 4 && l + 1 < c.num_layers) t = &m->layers[l + 1].q_qkv;
     if (!t) return;
-    const bool t_int = t->packed_i && !getenv("ZL_W4_FORCE_HALF") && zl_w4_int_kernel_fits(B, t->N, t->K);
+    const bool t_int = t->packed_i && !getenv("ZL_W4_FORCE_HALF") && zl_w4_int_layout_route(B, t->N, t->K) != 0;
     *ptr = t_int ? t->packed_i : t->packed;
     const size_t nb = zl_w4_packed_bytes(t->N, t->K, c.group_size);
     *bytes = nb < prefetch_cap() ? nb : prefetch_cap();
@@ -612,9 +664,19 @@ int w4_gemm(zl_llama* m, const void* x, int ldx, const W4Lin& w, const void* res
     zl_w4_fused_args_t a = {};
     a.x = x;
     a.ldx = ldx;
-    const bool use_int = w.packed_i && !getenv("ZL_W4_FORCE_HALF") && zl_w4_int_kernel_fits(B, w.N, w.K);
+    const int route = (w.packed_i && !getenv("ZL_W4_FORCE_HALF")) ? zl_w4_int_layout_route(B, w.N, w.K) : 0;
+    const bool use_int = route != 0;
     a.packed = use_int ? w.packed_i : w.packed;
     a.variant = use_int ? 1 : 0;
+    if (route == 4 && ln_w) {
+        // the tcgen05 kernel reads x through the TMA engine: the RMSNorm runs as its own kernel (reference order,
+        // block.cpp:125,131) into the matching rows of xn
+        const size_t off = (const char*)x - (const char*)m->h;
+        void* xn = (char*)m->xn + off;
+        RCHECK(zl_rmsnorm(x, ln_w, xn, B, w.K, c.eps, 1.f, c.dtype, force_no_pdl ? 0 : c.use_pdl, m->stream));
+        a.x = xn;
+        ln_w = nullptr;
+    }
     if (layer >= 0) {
         size_t nb = 0;
         prefetch_target(m, layer, slot, B, &a.prefetch_ptr, &nb);
@@ -644,7 +706,7 @@ int w4_gemm(zl_llama* m, const void* x, int ldx, const W4Lin& w, const void* res
         a.sin = m->sinb + (size_t)row0 * c.dim_head;
         a.q_out = (char*)m->q + (size_t)row0 * m->hq * c.dim_head * 2;
         a.token_batch = m->cur_tb + row0;
-        a.placement = m->d_pos + row0;
+        a.placement = m->cur_pos + row0;
         a.k_addrs = rope_layer->k_addrs;
         a.v_addrs = rope_layer->v_addrs;
         a.num_heads = m->hq;
@@ -655,98 +717,7 @@ int w4_gemm(zl_llama* m, const void* x, int ldx, const W4Lin& w, const void* res
     return zl_w4a16_gemm_fused(&a, m->stream);
 }
 
-int build_mega_layers(zl_llama* m) {
-    const auto& c = m->cfg;
-    if (!(c.quant_type == 5 || c.quant_type == 6)) return ZL_OK;
-    std::vector<MegaLayer> host(c.num_layers);
-    for (int l = 0; l < c.num_layers; ++l) {
-        Layer& L = m->layers[l];
-        const W4Lin* lin[4] = {&L.q_qkv, &L.q_o, &L.q_gu, &L.q_down};
-        for (int i = 0; i < 4; ++i) {
-            if (!lin[i]->packed_i) return ZL_OK;   // some GEMM has no integer layout: the persistent kernel is not used
-            host[l].packed[i] = static_cast<const uint8_t*>(lin[i]->packed_i);
-            host[l].bias[i] = static_cast<const __half*>(lin[i]->bias);
-        }
-        host[l].ln_attn = static_cast<const __half*>(L.ln_attn);
-        host[l].ln_ff = static_cast<const __half*>(L.ln_ff);
-        host[l].k_addrs = reinterpret_cast<__half* const*>(L.k_addrs);
-        host[l].v_addrs = reinterpret_cast<__half* const*>(L.v_addrs);
-    }
-    RCHECK(dmalloc((void**)&m->d_mega_layers, host.size() * sizeof(MegaLayer)));
-    ZL_CHECK_CUDA(cudaMemcpy(m->d_mega_layers, host.data(), host.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice));
-    RCHECK(dmalloc((void**)&m->d_mega_sync, 16));
-    ZL_CHECK_CUDA(cudaMemset(m->d_mega_sync, 0, 16));
-    if (getenv("ZL_MEGA_TRACE")) {
-        RCHECK(dmalloc((void**)&m->d_mega_trace, 512 * 8));
-        ZL_CHECK_CUDA(cudaMemset(m->d_mega_trace, 0, 512 * 8));
-    }
-    return ZL_OK;
-}
-
-static int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
-
-// fills the parameter block of the persistent kernel; stages = 0 when this (B, bucket) cannot use it
-int mega_plan(zl_llama* m, int B, int len_bucket, MegaParams* p) {
-    const auto& c = m->cfg;
-    if (!m->d_mega_layers || c.tp_size > 1 || c.dtype != ZL_F16 || B > 8 || getenv("ZL_NO_MEGA")) return 0;
-    if (!(c.dim_head == 64 || c.dim_head == 128)) return 0;
-    const int splits = (len_bucket + 255) / 256;
-    const int hgroups = (m->hq / m->hkv + 7) / 8;
-    if (splits > 64 || (long long)B * m->hkv * hgroups * splits > 16LL * num_sms()) return 0;
-    MegaParams q{};
-    q.layers = m->d_mega_layers;
-    q.num_layers = c.num_layers;
-    q.mc = B;
-    const int d = c.dim_head;
-    const int N[4] = {(m->hq + 2 * m->hkv) * d, c.dim_model, 2 * m->ff, c.dim_model};
-    const int K[4] = {c.dim_model, m->hq * d, c.dim_model, m->ff};
-    int k_max = 0;
-    for (int i = 0; i < 4; ++i) {
-        q.gN[i] = N[i];
-        q.gK[i] = K[i];
-        q.gTall[i] = (N[i] / 32 <= num_sms() && K[i] / kW4GroupK >= 32) ? 1 : 0;   // same rule as the per-GEMM kernel
-        if (K[i] % kW4GroupK != 0 || N[i] % 32 != 0 || K[i] / kW4GroupK > 128) return 0;
-        k_max = K[i] > k_max ? K[i] : k_max;
-    }
-    q.num_heads = m->hq;
-    q.num_kv_heads = m->hkv;
-    q.dim_head = d;
-    q.eps = c.eps;
-    q.attn_scale = 1.0f / sqrtf((float)d);
-    q.h = static_cast<__half*>(m->h);
-    q.q = static_cast<__half*>(m->q);
-    q.ao = static_cast<__half*>(m->ao);
-    q.act = static_cast<__half*>(m->act);
-    q.cos = m->cosb;
-    q.sin = m->sinb;
-    q.token_batch = m->d_iota;
-    q.placement = m->d_pos;
-    q.buf_lens = m->d_lens;
-    q.attn_splits = splits;
-    if (splits > 1) {
-        const size_t vheads = (size_t)B * m->hq;
-        if (vheads * splits * (d + 2) * sizeof(float) > m->attn_ws_bytes) return 0;
-        q.part_o = static_cast<float*>(m->attn_ws);
-        q.part_m = q.part_o + vheads * splits * d;
-        q.part_l = q.part_m + vheads * splits;
-    }
-    q.sync = m->d_mega_sync;
-    q.trace = m->d_mega_trace;
-    int stages = 0;
-    if (mega_smem_bytes(B, k_max, d, 4) <= 232448) stages = 4;
-    else if (mega_smem_bytes(B, k_max, d, 3) <= 232448) stages = 3;
-    *p = q;
-    return stages;
-}
+static int num_sms() { return device_sm_count(); }
 
 // ZL_DEBUG_SKIP (bit mask, timing experiments only -- results are wrong when set):
 // 1 attention, 2 qkv GEMM, 4 o GEMM, 8 gate/up GEMM, 16 down GEMM, 32 lm_head, 64 rope/append kernel
@@ -835,7 +806,7 @@ int prefill_layers_dual(zl_llama* m, const PrefillChunk& pf) {
                 void* qp = rows(m->qkv, r0[h], (size_t)(m->hq + 2 * m->hkv) * d * 2);
                 RCHECK(w4_gemm(m, hp, D, L.q_qkv, nullptr, qp, nh[h], ZL_EPI_NONE, L.ln_attn, nullptr, -1, -1, 0, 1));
                 RCHECK(zl_qkv_rope_append(m->cosb + (size_t)r0[h] * d, m->sinb + (size_t)r0[h] * d, qp,
-                                          rows(m->q, r0[h], (size_t)m->hq * d * 2), m->cur_tb + r0[h], m->d_pos + r0[h],
+                                          rows(m->q, r0[h], (size_t)m->hq * d * 2), m->cur_tb + r0[h], m->cur_pos + r0[h],
                                           L.k_addrs, L.v_addrs, nh[h], m->hq, m->hkv, d, 1, 1, m->d_lens, dt, 0, cs));
             }
             // causal rows r0.. of the chunk's mask; keys of BOTH halves are visible as far as the mask allows, so half 1
@@ -884,26 +855,22 @@ int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* p
     }
     const float scale = 1.0f / sqrtf((float)d);   // attention.cpp:89
 
-    // grid-barrier counter of the persistent kernel: zeroed first so that the kernel chain below stays kernel->kernel
-    if (m->d_mega_sync && c.fuse >= 3) ZL_CHECK_CUDA(cudaMemsetAsync(m->d_mega_sync, 0, 4, st));
     if (pf) {
-        k_prefill_setup<<<8, 256, 0, st>>>(m->d_pos, m->d_tb, m->d_lens, m->d_mask, pf->task, pf->pos0, pf->n);
+        k_prefill_setup<<<8, 256, 0, st>>>(m->d_pf_pos, m->d_tb, m->d_lens, m->d_mask, pf->task, pf->pos0, pf->n);
         ZL_CHECK_LAUNCH();
     } else {
         ZL_CHECK_CUDA(launch(k_lens_from_pos, dim3(cdiv(B, 64)), dim3(64), 0, st, false, (const int32_t*)m->d_pos,
                              m->d_lens, B, g_w4_trace));
     }
     m->cur_tb = pf ? m->d_tb : m->d_iota;
-    RCHECK(zl_rope_cos_sin(m->d_pos, m->cosb, m->sinb, B, d, c.rope_theta, c.rope_llama3_factor,
+    m->cur_pos = pf ? m->d_pf_pos : m->d_pos;
+    m->cur_tokens = pf ? m->d_pf_tokens : m->d_tokens;
+    RCHECK(zl_rope_cos_sin(m->cur_pos, m->cosb, m->sinb, B, d, c.rope_theta, c.rope_llama3_factor,
                            c.rope_low_freq_factor, c.rope_high_freq_factor, c.rope_orig_ctx, 1, st));
-    RCHECK(zl_embedding(m->d_tokens, m->emb, m->h, B, D, c.vocab_size, dt, 0, st));
-    MegaParams mp;
-    const int mega_stages = (w4 && c.fuse >= 3 && !skip && !pf) ? mega_plan(m, B, len_bucket, &mp) : 0;
-    m->mega_used = mega_stages != 0;
-    if (mega_stages) ZL_CHECK_CUDA(launch_llama_mega(mp, mega_stages, pdl != 0, st));
+    RCHECK(zl_embedding(m->cur_tokens, m->emb, m->h, B, D, c.vocab_size, dt, 0, st));
     const bool dual = pf && prefill_dual_enabled(m, pf->n);
     if (dual) RCHECK(prefill_layers_dual(m, *pf));
-    for (int l = 0; l < ((mega_stages || dual) ? 0 : c.num_layers); ++l) {
+    for (int l = 0; l < (dual ? 0 : c.num_layers); ++l) {
         Layer& L = m->layers[l];
         if (w4) {
             const void* xin = m->xn;
@@ -927,7 +894,7 @@ int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* p
             RCHECK(dense_or_w8(m, m->xn, L.d_qkv, m->qkv, B, pdl));
         }
         if (!(w4 && c.fuse >= 2) && !(skip & 64))
-            RCHECK(zl_qkv_rope_append(m->cosb, m->sinb, m->qkv, m->q, m->cur_tb, m->d_pos, L.k_addrs, L.v_addrs, B,
+            RCHECK(zl_qkv_rope_append(m->cosb, m->sinb, m->qkv, m->q, m->cur_tb, m->cur_pos, L.k_addrs, L.v_addrs, B,
                                       m->hq, m->hkv, d, 1, 1, m->d_lens, dt, pdl, st));
         if (!(skip & 1)) {
             const void* pfp = nullptr;
@@ -1070,7 +1037,7 @@ extern "C" int zl_llama_create(const zl_llama_config_t* cfg, zl_llama_t** out) {
                        cfg->dim_ff % cfg->tp_size == 0 && cfg->vocab_size % cfg->tp_size == 0);
     ZL_CHECK_SUPPORTED(!(cfg->quant_type == 5 || cfg->quant_type == 6) || cfg->group_size == zl::kW4GroupK);
     ZL_CHECK_ARG(cfg->fuse >= 0 && cfg->fuse <= 3);
-    ZL_CHECK_ARG(cfg->prefill_chunk >= 0 && cfg->prefill_chunk <= 32);
+    ZL_CHECK_ARG(cfg->prefill_chunk >= 0 && cfg->prefill_chunk <= 2048);
     ZL_CHECK_SUPPORTED(cfg->fuse < 2 || cfg->dim_head % 32 == 0);
     RCHECK(zl_prepare());
     zl_llama* m = new zl_llama();
@@ -1109,8 +1076,7 @@ extern "C" void zl_llama_destroy(zl_llama_t* m) {
     }
     for (void* p : {m->emb, m->lm_head_tied ? nullptr : m->lm_head, m->ln_f, m->h, m->xn, m->qkv, m->q, m->ao, m->act,
                     m->pend, m->gu, (void*)m->logits, (void*)m->cosb, (void*)m->sinb, (void*)m->d_tokens,
-                    (void*)m->d_pos, (void*)m->d_lens, (void*)m->d_next, (void*)m->d_iota, m->attn_ws, m->argmax_ws, (void*)m->d_mega_layers, (void*)m->d_mega_sync,
-                    (void*)m->d_mega_trace, (void*)m->d_tb, (void*)m->d_mask, m->xq, (void*)m->xs})
+                    (void*)m->d_pos, (void*)m->d_lens, (void*)m->d_next, (void*)m->d_iota, m->attn_ws, m->argmax_ws, (void*)m->d_tb, (void*)m->d_mask, m->xq, (void*)m->xs})
         if (p) cudaFree(p);
     if (m->reduce_stream) {
         cudaStreamSynchronize(m->reduce_stream);
@@ -1120,6 +1086,11 @@ extern "C" void zl_llama_destroy(zl_llama_t* m) {
         cudaStreamDestroy(m->reduce_stream);
     }
     if (m->h_stage) cudaFreeHost(m->h_stage);
+    if (m->h_ring) cudaFreeHost(m->h_ring);
+    for (cudaEvent_t e : m->ring_ev)
+        if (e) cudaEventDestroy(e);
+    for (void* p : {(void*)m->d_pf_tokens, (void*)m->d_pf_pos})
+        if (p) cudaFree(p);
     cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -1151,7 +1122,6 @@ extern "C" int zl_llama_finalize(zl_llama_t* m) {
         if (!m->layers[l].ln_attn) RCHECK(finalize_layer(m, l));
     RCHECK(finalize_globals(m));
     RCHECK(alloc_runtime(m));
-    RCHECK(build_mega_layers(m));
     m->finalized = true;
     return ZL_OK;
 }
@@ -1246,16 +1216,23 @@ extern "C" int zl_llama_set_state(zl_llama_t* m, const int32_t* tokens_host, con
         zl_set_last_error(__FILE__, __LINE__, "model not finalized");
         return ZL_ERR_STATE;
     }
+    const int slot = m->ring_next;
+    m->ring_next = (slot + 1) % zl_llama::kStageSlots;
+    if (m->ring_used[slot]) ZL_CHECK_CUDA(cudaEventSynchronize(m->ring_ev[slot]));   // its previous copies have executed
+    int32_t* hs = m->h_ring + (size_t)slot * 2 * m->cfg.max_batch;
     int mx = 0;
     for (int i = 0; i < B; ++i) {
         ZL_CHECK_ARG(positions_host[i] >= 0 && positions_host[i] < m->cfg.max_seq);
-        m->h_stage[i] = tokens_host[i];
-        m->h_stage[B + i] = positions_host[i];
+        ZL_CHECK_ARG(tokens_host[i] >= 0 && tokens_host[i] < m->cfg.vocab_size);
+        hs[i] = tokens_host[i];
+        hs[B + i] = positions_host[i];
         if (positions_host[i] + 1 > mx) mx = positions_host[i] + 1;
     }
     m->cur_max_len = mx;
-    ZL_CHECK_CUDA(cudaMemcpyAsync(m->d_tokens, m->h_stage, B * 4, cudaMemcpyHostToDevice, m->stream));
-    ZL_CHECK_CUDA(cudaMemcpyAsync(m->d_pos, m->h_stage + B, B * 4, cudaMemcpyHostToDevice, m->stream));
+    ZL_CHECK_CUDA(cudaMemcpyAsync(m->d_tokens, hs, B * 4, cudaMemcpyHostToDevice, m->stream));
+    ZL_CHECK_CUDA(cudaMemcpyAsync(m->d_pos, hs + B, B * 4, cudaMemcpyHostToDevice, m->stream));
+    ZL_CHECK_CUDA(cudaEventRecord(m->ring_ev[slot], m->stream));
+    m->ring_used[slot] = true;
     return ZL_OK;
 }
 
@@ -1281,15 +1258,7 @@ extern "C" int zl_llama_decode(zl_llama_t* m, const int32_t* tokens_host, const 
     if (logits_host)   // (B, vocab/tp) of this rank's shard
         ZL_CHECK_CUDA(cudaMemcpyAsync(logits_host, m->logits, (size_t)B * m->vshard * 4, cudaMemcpyDeviceToHost,
                                       m->stream));
-    const int mb = m->cfg.max_batch;
-    m->h_stage[4 * mb] = 0;
-    if (m->mega_used)   // sticky abort flag of the persistent kernel travels with the result
-        ZL_CHECK_CUDA(cudaMemcpyAsync(m->h_stage + 4 * mb, m->d_mega_sync + 1, 4, cudaMemcpyDeviceToHost, m->stream));
     ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
-    if (m->h_stage[4 * mb] != 0) {
-        zl_set_last_error(__FILE__, __LINE__, "persistent decode kernel aborted: a grid barrier timed out");
-        return ZL_ERR_STATE;
-    }
     for (int i = 0; i < B; ++i) next_tokens_host[i] = m->h_stage[3 * B + i];
     return ZL_OK;
 }
@@ -1363,14 +1332,6 @@ extern "C" int zl_llama_bench_gemms(zl_llama_t* m, int B, int iters, float* ms, 
 extern "C" int zl_llama_sync(zl_llama_t* m) {
     ZL_CHECK_ARG(m);
     ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
-    if (m->d_mega_sync) {
-        unsigned words[2] = {0, 0};
-        ZL_CHECK_CUDA(cudaMemcpy(words, m->d_mega_sync, 8, cudaMemcpyDeviceToHost));
-        if (words[1]) {
-            zl_set_last_error(__FILE__, __LINE__, "persistent decode kernel aborted: a grid barrier timed out");
-            return ZL_ERR_STATE;
-        }
-    }
     return ZL_OK;
 }
 
@@ -1395,7 +1356,7 @@ extern "C" int zl_llama_prefill(zl_llama_t* m, int task, const int32_t* tokens_h
             ZL_CHECK_ARG(tokens_host[c0 + i] >= 0 && tokens_host[c0 + i] < m->cfg.vocab_size);
             h_tok[i] = tokens_host[c0 + i];
         }
-        ZL_CHECK_CUDA(cudaMemcpyAsync(m->d_tokens, h_tok, cn * 4, cudaMemcpyHostToDevice, m->stream));
+        ZL_CHECK_CUDA(cudaMemcpyAsync(m->d_pf_tokens, h_tok, cn * 4, cudaMemcpyHostToDevice, m->stream));
         PrefillChunk pc{task, pos0 + c0, cn, c0 + cn == n};
         RCHECK(enqueue_step(m, 1, 0, &pc));
     }
@@ -1405,17 +1366,6 @@ extern "C" int zl_llama_prefill(zl_llama_t* m, int task, const int32_t* tokens_h
     ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
     *next_token_host = m->h_stage[3 * m->cfg.max_batch];
     if (pos0 + n > m->cur_max_len) m->cur_max_len = pos0 + n;
-    return ZL_OK;
-}
-
-extern "C" int zl_llama_mega_trace(zl_llama_t* m, unsigned long long* out, int n_words) {
-    ZL_CHECK_ARG(m && out && n_words > 0 && n_words <= 512);
-    if (!m->d_mega_trace) {
-        zl_set_last_error(__FILE__, __LINE__, "no trace buffer: set ZL_MEGA_TRACE=1 before zl_llama_finalize");
-        return ZL_ERR_STATE;
-    }
-    ZL_CHECK_CUDA(cudaStreamSynchronize(m->stream));
-    ZL_CHECK_CUDA(cudaMemcpy(out, m->d_mega_trace, (size_t)n_words * 8, cudaMemcpyDeviceToHost));
     return ZL_OK;
 }
 

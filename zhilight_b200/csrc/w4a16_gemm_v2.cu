@@ -390,16 +390,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((NT <= 2 && WARPS == 8) ? 2 : 1))
     }
 }
 
-static int v2_num_sms() {
-    static int n_sm = 0;
-    if (n_sm == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (n_sm <= 0) n_sm = 148;
-    }
-    return n_sm;
-}
+static int v2_num_sms() { return device_sm_count(); }
 
 template <int NT, bool NORM, bool XC, int WARPS, int STAGES>
 static cudaError_t launch_v2_t(const W4Params& p, bool pdl, cudaStream_t stream) {

@@ -51,9 +51,9 @@ struct V3Smem {
     static constexpr int kRedFloats = WARPS * RT * 32;                     // per sub-CTA, per buffer
     static constexpr int kBarOff = kRingBytes;
     static constexpr int kRedOff = kBarOff + kWarpsTotal * STAGES * 8;
-    static constexpr int kSsOff = kRedOff + SUBS * kRedBufs * kRedFloats * 4;   // [warps total][NT*8]
-    static constexpr int kRstdOff = kSsOff + kWarpsTotal * NT * 8 * 4;          // [NT*8]
-    static constexpr int kXOff = (kRstdOff + NT * 8 * 4 + 127) & ~127;
+    static constexpr int kSsOff = kRedOff + SUBS * kRedBufs * kRedFloats * 4;   // [warps total][NT*8] sum x^2 | [warps total][NT*8] poison
+    static constexpr int kRstdOff = kSsOff + 2 * kWarpsTotal * NT * 8 * 4;      // [NT*8] rstd | [NT*8] poison
+    static constexpr int kXOff = (kRstdOff + 2 * NT * 8 * 4 + 127) & ~127;
     static constexpr int kBytes = kXOff;
 };
 // staged activations (whole K): mc rows of hi bytes, mc rows of lo bytes, then the group table
@@ -170,6 +170,11 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
     float* red = reinterpret_cast<float*>(smem + S::kRedOff) + sub * (S::kRedBufs * S::kRedFloats);
     float* s_ss = reinterpret_cast<float*>(smem + S::kSsOff);
     float* s_rstd = reinterpret_cast<float*>(smem + S::kRstdOff);
+    // Inf / NaN activations: the integer decomposition cannot carry them, so a group whose maximum is non-finite
+    // poisons every output of its token with NaN (the reference GEMV, q_gemm_k_major.cu:127-173, yields NaN or +-Inf
+    // there) instead of silently contributing zero.
+    float* s_pw = s_ss + WT * (NT * 8);       // per (warp, token): 0 or NaN
+    float* s_poison = s_rstd + NT * 8;        // per token
     const int row_b = v3_row_bytes(p.K);
     uint8_t* xs_hi = smem + S::kXOff;                                    // [tok][row_b]
     uint8_t* xs_lo = xs_hi + p.mc * row_b;                               // [tok][row_b]
@@ -247,6 +252,7 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
             if (gi < G) raw[gl] = ld_cg_u2(p.x + (size_t)tok * p.ldx + gi * kW4GroupK + lane * 4);
         }
         float sq = 0.f;
+        bool bad = false;
 #pragma unroll
         for (int gl = 0; gl < kMaxNg; ++gl) {
             const int gi = warp + gl * WT;
@@ -262,12 +268,15 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
                     h23 = __hmul2(h23, *reinterpret_cast<const __half2*>(&lnw[gl].y));
                 }
                 const float2 a = __half22float2(h01), b = __half22float2(h23);
-                const float amax_l = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(b.x), fabsf(b.y)));
-                // non-negative floats order like their bit patterns: one REDUX instead of a shuffle tree
-                const uint32_t amax_bits = __reduce_max_sync(0xffffffffu, __float_as_uint(amax_l));
+                // non-negative floats order like their bit patterns (and NaN patterns sort above Inf, which fmaxf would
+                // drop): integer maxima, then one REDUX instead of a shuffle tree
+                const uint32_t amax_l = max(max(__float_as_uint(fabsf(a.x)), __float_as_uint(fabsf(a.y))),
+                                            max(__float_as_uint(fabsf(b.x)), __float_as_uint(fabsf(b.y))));
+                const uint32_t amax_bits = __reduce_max_sync(0xffffffffu, amax_l);
                 // 2^e with m = x * 2^-e in (-2^15, 2^15): e = floor(log2 amax) - 14
                 const uint32_t ex = (amax_bits >> 23) & 0xffu;
-                const bool zero = ex < 20u || ex == 0xffu;   // all-zero / tiny / non-finite group -> contributes 0
+                const bool zero = ex < 20u || ex == 0xffu;   // all-zero group -> 0; non-finite group -> poisons the token
+                bad |= ex == 0xffu;                          // (a NaN's bit pattern is above Inf's: REDUX max keeps it)
                 // PACK keeps one bit of headroom (|m| <= 2^14) so that the rounded-up high digit still fits int8
                 constexpr uint32_t kE = PACK ? 13u : 14u;
                 const float sg = zero ? 1.0f : __uint_as_float((ex - kE) << 23);
@@ -291,19 +300,24 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
             sq = warp_sum(sq);
             if (lane == 0) s_ss[warp * (NT * 8) + tok] = sq;
         }
+        if (lane == 0) s_pw[warp * (NT * 8) + tok] = bad ? __int_as_float(0x7fc00000) : 0.f;
     }
     if (p.dbg & 8) stamp();   // warp 0 finished its groups (loads landed + quantised)
     __syncthreads();
     if (p.dbg & 8) stamp();   // all warps staged
-    if (NORM) {
-        if (threadIdx.x < p.mc) {
+    if (threadIdx.x < p.mc) {
+        float po = 0.f;
+#pragma unroll
+        for (int w = 0; w < WT; ++w) po += s_pw[w * (NT * 8) + threadIdx.x];
+        s_poison[threadIdx.x] = po;
+        if (NORM) {
             float v = 0.f;
 #pragma unroll
             for (int w = 0; w < WT; ++w) v += s_ss[w * (NT * 8) + threadIdx.x];
             s_rstd[threadIdx.x] = rsqrtf(v / (float)p.K + p.eps);
         }
-        __syncthreads();
     }
+    __syncthreads();
     stamp();
 
     int c_slot = 0;
@@ -483,6 +497,8 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
                     gate *= s_rstd[tok];
                     up *= s_rstd[tok];
                 }
+                gate += s_poison[tok];
+                up += s_poison[tok];
                 if (p.bias) {
                     gate += __half2float(p.bias[n0 + rg]);
                     up += __half2float(p.bias[n0 + rg + 8]);
@@ -504,6 +520,8 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
                     lo *= s_rstd[tok];
                     hi *= s_rstd[tok];
                 }
+                lo += s_poison[tok];
+                hi += s_poison[tok];
                 if (p.bias) {
                     lo += __half2float(p.bias[n0 + rlo]);
                     hi += __half2float(p.bias[n0 + rlo + 8]);
@@ -542,6 +560,7 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
                 const int tok = e >> 5, row = e & 31;
                 float v = sum_red(tok * 32 + row);
                 if (NORM) v *= s_rstd[tok];
+                v += s_poison[tok];
                 if (p.bias) v += __half2float(p.bias[n0 + row]);
                 __half h = __float2half_rn(v);
                 if (p.epi == ZL_EPI_RESIDUAL)
@@ -554,16 +573,7 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
     }
 }
 
-static int v3_num_sms() {
-    static int n_sm = 0;
-    if (n_sm == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (n_sm <= 0) n_sm = 148;
-    }
-    return n_sm;
-}
+static int v3_num_sms() { return device_sm_count(); }
 
 constexpr int kV3Budget = 231000;   // one CTA per SM (227 KB usable + 1 KB reserved)
 

@@ -1,0 +1,626 @@
+// W4A16 GEMM on the 5th-generation tensor cores: tcgen05.mma (kind::f16) with TMEM accumulators, tensor-TMA for the
+// activations, bulk-TMA for the int4 weight blocks.  Serves every M the exact-integer mma.sync kernel
+// (w4a16_gemm_v3.cu) cannot stage: batch 17..256 decode and chunked prefill.
+//
+// Replaces the reference's Marlin kernel (src/nn/quant/marlin/gptq_marlin.cu:425-1620), the M <= 40 GEMV tiles of
+// KERNEL_gemm_warp_reduce (src/nn/quant/gptq/q_gemm_k_major.cu:176-237, 580-686: the weight matrix is streamed
+// ceil(M/16) times) and the M > 40 route "dequantise the whole matrix to fp16 in HBM, then cuBLASLt"
+// (q_gemm_k_major.cu:843-905, 1083-1100).  Same arithmetic contract as that route: w = (q - z) * s rounded to fp16
+// once, fp16 x fp16 products, fp32 accumulation over all of K.
+//
+// One CTA per SM, persistent over work items (128 weight rows x a k-slice); 15 warps in five roles:
+//   warp 0      raw producer : cp.async.bulk (UBLKCP) of 4 ZLW4I blocks (32 rows x 128 k, 2128 B each) per stage
+//   warp 1      x producer   : cp.async.bulk.tensor.2d (UTMALDG), box 64 k x NTOK tokens, SWIZZLE_128B, OOB rows = 0
+//   warp 2      MMA issuer   : one thread, 8 x tcgen05.mma 128 x NTOK x 16 per 128-k stage, tcgen05.commit frees stages
+//   warps 3-10  dequant      : nibbles -> fp16 (PRMT 0x64xx / 0x54xx magic, exact q - z, one HMUL2 by the group scale)
+//                              written as the K-major SWIZZLE_128B A operand, fence.proxy.async, mbarrier arrive
+//   warps 11-14 epilogue     : tcgen05.ld 32x32b of their TMEM lane quadrant, bias / residual / SwiGLU / qkv-RoPE-KV
+// The accumulator is double-buffered in TMEM (2 x NTOK columns), so the drain of item i overlaps the mainloop of
+// item i+1.  GEMMs with fewer than #SM row tiles split K across CTAs; the partial sums meet in an fp32 workspace and
+// the last CTA of a tile reduces them in split order (deterministic) before the epilogue.
+#include "common.cuh"
+#include "w4_layout.cuh"
+#include "w4_params.h"
+
+#include <cuda.h>
+
+#include <cstdlib>
+
+namespace zl {
+
+constexpr int kTcRows = 128;                        // weight rows per tile = UMMA M = TMEM lanes
+constexpr int kTcRawStage = 4 * kW4BlockBytes;      // 4 blocks of 32 rows
+constexpr int kTcAStage = 2 * kTcRows * 128;        // [k atom (64 k)][row][128 B]
+constexpr int kTcWarpRaw = 0, kTcWarpX = 1, kTcWarpMma = 2, kTcWarpDq0 = 3, kTcDqWarps = 8, kTcWarpEpi0 = 11;
+constexpr int kTcThreads = 15 * 32;
+constexpr int kTcDqThreads = kTcDqWarps * 32;
+
+template <int NTOK>
+struct TcCfg {
+    static constexpr int AS = NTOK <= 32 ? 4 : (NTOK <= 64 ? 3 : 2);   // A / x stages
+    static constexpr int RS = NTOK <= 128 ? 4 : 3;                     // raw weight stages
+    static constexpr int kXStage = 2 * NTOK * 128;                     // [k atom][token][128 B]
+    static constexpr int kAOff = 0;
+    static constexpr int kXOff = kAOff + AS * kTcAStage;
+    static constexpr int kRawOff = kXOff + AS * kXStage;
+    static constexpr int kBarOff = (kRawOff + RS * kTcRawStage + 15) & ~15;
+    static constexpr int kNumBars = 2 * RS + 3 * AS + 4;
+    static constexpr int kMiscOff = kBarOff + kNumBars * 8;
+    static constexpr int kBytes = kMiscOff + 16 + 1024;                // + slack for the manual 1024-byte alignment
+    static constexpr int kTmemCols = 2 * NTOK < 32 ? 32 : 2 * NTOK;    // power of two for NTOK in {16,32,64,128,256}
+};
+
+struct alignas(64) W4TcParams {
+    CUtensorMap xmap;           // x (M, K) fp16 row-major, box {64, NTOK}, 128-byte swizzle
+    const uint8_t* packed;      // ZLW4I
+    const __half* bias;         // indexed by PACKED row
+    const __half* residual;
+    __half* y;
+    int M, N, K, epi, S;        // S = k splits
+    float* ws;                  // [tile][split][M][128] fp32 partial sums (S > 1)
+    unsigned* counters;         // [tile] arrivals (S > 1), left at zero
+    unsigned* err;              // watchdog code
+    const float* cos;
+    const float* sin;
+    __half* q_out;
+    const int32_t* token_batch;
+    const int32_t* placement;
+    __half* const* k_addrs;
+    __half* const* v_addrs;
+    int num_heads, num_kv_heads, dim_head;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a protocol bug must not hang the GPU (2 s, then the watchdog code is published and the kernel traps)
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, unsigned* err, unsigned code) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = globaltimer_ns();
+    while (!mbar_try_wait(bar, parity)) {
+        if (globaltimer_ns() - t0 > 2000000000ull) {
+            if (err) atomicExch(err, code);
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start address
+// >> 4, LBO (unused for swizzled K-major, canonical value 1), SBO = 1024 B between 8-row groups, version 1, layout 2.
+__device__ __forceinline__ uint64_t tc_desc_sw128(uint32_t saddr) {
+    uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor, kind::f16: D f32 (bits 4-5 = 1), A/B f16 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr uint32_t tc_idesc_f16(int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// One 32-bit ZLW4I word = 4 consecutive k of row g (low nibbles) and of row g + 8 (high nibbles) -> 2 x 2 half2.
+// 0x64xx is 1024 + x for x < 1024; 0x54xx is 64 + x / 16: the high nibble never has to be shifted.
+__device__ __forceinline__ void tc_dequant_word(uint32_t w, __half2 c_lo, __half2 s_lo, __half2 c_hi, __half2 s_hi,
+                                                uint32_t (&lo)[2], uint32_t (&hi)[2]) {
+    const uint32_t wl = w & 0x0f0f0f0fu, wh = w & 0xf0f0f0f0u;
+    uint32_t a0 = __byte_perm(wl, 0x64646464u, 0x4140), a1 = __byte_perm(wl, 0x64646464u, 0x4342);
+    uint32_t b0 = __byte_perm(wh, 0x54545454u, 0x4140), b1 = __byte_perm(wh, 0x54545454u, 0x4342);
+    __half2 r;
+    r = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&a0), c_lo), s_lo);
+    lo[0] = *reinterpret_cast<uint32_t*>(&r);
+    r = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&a1), c_lo), s_lo);
+    lo[1] = *reinterpret_cast<uint32_t*>(&r);
+    r = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&b0), c_hi), s_hi);
+    hi[0] = *reinterpret_cast<uint32_t*>(&r);
+    r = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&b1), c_hi), s_hi);
+    hi[1] = *reinterpret_cast<uint32_t*>(&r);
+}
+
+// ---- epilogue of 16 tokens (c0 .. c0+15) for the weight row owned by this lane -----------------------------------------
+// Packed row p = tile * 128 + 32 * quadrant + lane.  Inside a 32-row block, rows (16 tt + g) and (16 tt + g + 8) are
+// partners (gate / up, RoPE low / high half): lane and lane + 8.
+__device__ __forceinline__ void tc_epilogue16(const W4TcParams& p, int prow, int lane, int c0, float (&v)[16]) {
+    const float b = p.bias ? __half2float(p.bias[prow]) : 0.f;
+    if (p.epi == ZL_EPI_SWIGLU) {
+        const int n_out = p.N / 2;
+        const int col = (prow >> 5) * 16 + ((lane >> 4) << 3) + (lane & 7);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float mine = __half2float(__float2half_rn(v[i] + b));
+            const float up = __shfl_down_sync(0xffffffffu, mine, 8);
+            const int tok = c0 + i;
+            if (!(lane & 8) && tok < p.M) p.y[(size_t)tok * n_out + col] = __float2half_rn(silu_f(mine) * up);
+        }
+    } else if (p.epi == ZL_EPI_QKV_ROPE) {
+        const int d = p.dim_head, half_dim = d / 2, tiles_per_head = d / 32;
+        const int st = prow >> 5, head = st / tiles_per_head, jt = st % tiles_per_head;
+        const int c = jt * 16 + ((lane >> 4) << 3) + (lane & 7);
+        const bool is_v = head >= p.num_heads + p.num_kv_heads;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float lo = __half2float(__float2half_rn(v[i] + b));
+            const float hi = __shfl_down_sync(0xffffffffu, lo, 8);
+            const int tok = c0 + i;
+            if ((lane & 8) || tok >= p.M) continue;
+            __half olo, ohi;
+            if (is_v) {
+                olo = __float2half_rn(lo);
+                ohi = __float2half_rn(hi);
+            } else {
+                const float* cs = p.cos + (size_t)tok * d;
+                const float* sn = p.sin + (size_t)tok * d;
+                olo = __float2half_rn(lo * cs[c] - hi * sn[c]);
+                ohi = __float2half_rn(hi * cs[c + half_dim] + lo * sn[c + half_dim]);
+            }
+            if (head < p.num_heads) {
+                __half* dst = p.q_out + ((size_t)tok * p.num_heads + head) * d;
+                dst[c] = olo;
+                dst[c + half_dim] = ohi;
+            } else {
+                const int pl = p.placement[tok];
+                if (pl >= 0) {
+                    const bool is_k = !is_v;
+                    const int hk = is_k ? head - p.num_heads : head - p.num_heads - p.num_kv_heads;
+                    __half* base = (is_k ? p.k_addrs : p.v_addrs)[p.token_batch[tok]];
+                    __half* dst = base + ((size_t)pl * p.num_kv_heads + hk) * d;
+                    dst[c] = olo;
+                    dst[c + half_dim] = ohi;
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int tok = c0 + i;
+            if (tok >= p.M) continue;
+            __half h = __float2half_rn(v[i] + b);
+            if (p.epi == ZL_EPI_RESIDUAL)
+                h = __float2half_rn(__half2float(h) + __half2float(p.residual[(size_t)tok * p.N + prow]));
+            p.y[(size_t)tok * p.N + prow] = h;
+        }
+    }
+}
+
+template <int NTOK>
+__global__ void __launch_bounds__(kTcThreads, 1) k_w4a16_tc(const __grid_constant__ W4TcParams p) {
+    using C = TcCfg<NTOK>;
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBarOff);
+    uint64_t* raw_full = bars;
+    uint64_t* raw_empty = raw_full + C::RS;
+    uint64_t* a_full = raw_empty + C::RS;
+    uint64_t* x_full = a_full + C::AS;
+    uint64_t* ax_empty = x_full + C::AS;
+    uint64_t* acc_full = ax_empty + C::AS;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + C::kMiscOff);
+    uint32_t* s_last = s_tmem + 1;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = p.K / kW4GroupK, n_tiles = p.N / kTcRows, S = p.S;
+    const int n_items = n_tiles * S;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < C::RS; ++i) {
+            mbar_init(&raw_full[i], 1);
+            mbar_init(&raw_empty[i], kTcDqThreads);
+        }
+        for (int i = 0; i < C::AS; ++i) {
+            mbar_init(&a_full[i], kTcDqThreads);
+            mbar_init(&x_full[i], 1);
+            mbar_init(&ax_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 128);
+        }
+        mbar_fence_init();
+    }
+    if (warp == kTcWarpMma) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                     "n"(C::kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    pdl_trigger();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == kTcWarpRaw) {
+        // ---------------- weight stream: constants, may run ahead of the predecessor kernel (PDL) ----------------
+        if (lane == 0) {
+            const uint64_t pol = l2_evict_first_policy();
+            int rs = 0;
+            uint32_t ph = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                const int tile = it / S, split = it % S;
+                const int g0 = (split * G) / S, g1 = ((split + 1) * G) / S;
+                for (int gi = g0; gi < g1; ++gi) {
+                    mbar_wait_wd(&raw_empty[rs], ph ^ 1u, p.err, 0x100 + rs);
+                    mbar_expect_tx(&raw_full[rs], kTcRawStage);
+                    uint8_t* dst = smem + C::kRawOff + rs * kTcRawStage;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        bulk_g2s_hint(dst + b * kW4BlockBytes,
+                                      p.packed + ((size_t)(tile * 4 + b) * G + gi) * kW4BlockBytes, kW4BlockBytes,
+                                      &raw_full[rs], pol);
+                    if (++rs == C::RS) {
+                        rs = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == kTcWarpX) {
+        // ---------------- activations: produced by the predecessor kernel ----------------
+        if (lane == 0) {
+            pdl_wait();
+            int as = 0;
+            uint32_t ph = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                const int split = it % S;
+                const int g0 = (split * G) / S, g1 = ((split + 1) * G) / S;
+                for (int gi = g0; gi < g1; ++gi) {
+                    mbar_wait_wd(&ax_empty[as], ph ^ 1u, p.err, 0x200 + as);
+                    mbar_expect_tx(&x_full[as], C::kXStage);
+                    uint8_t* dst = smem + C::kXOff + as * C::kXStage;
+                    tma_load_2d(dst, &p.xmap, gi * kW4GroupK, 0, &x_full[as]);
+                    tma_load_2d(dst + NTOK * 128, &p.xmap, gi * kW4GroupK + 64, 0, &x_full[as]);
+                    if (++as == C::AS) {
+                        as = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == kTcWarpMma) {
+        // ---------------- one thread issues every MMA of the CTA ----------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc_idesc_f16(NTOK);
+            int as = 0, acc = 0;
+            uint32_t ph = 0, acc_ph = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                const int split = it % S;
+                const int g0 = (split * G) / S, g1 = ((split + 1) * G) / S;
+                mbar_wait_wd(&acc_empty[acc], acc_ph ^ 1u, p.err, 0x300 + acc);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NTOK);
+                for (int gi = g0; gi < g1; ++gi) {
+                    mbar_wait_wd(&a_full[as], ph, p.err, 0x400 + as);
+                    mbar_wait_wd(&x_full[as], ph, p.err, 0x500 + as);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(smem + C::kAOff + as * kTcAStage);
+                    const uint32_t x_base = smem_u32(smem + C::kXOff + as * C::kXStage);
+#pragma unroll
+                    for (int ka = 0; ka < 2; ++ka) {
+                        const uint64_t ad = tc_desc_sw128(a_base + ka * (kTcRows * 128));
+                        const uint64_t xd = tc_desc_sw128(x_base + ka * (NTOK * 128));
+#pragma unroll
+                        for (int k16 = 0; k16 < 4; ++k16)   // 16 fp16 = 32 bytes along K inside the swizzle atom
+                            tc_mma_f16(d_tmem, ad + (uint64_t)(k16 * 2), xd + (uint64_t)(k16 * 2), idesc,
+                                       (gi > g0 || ka > 0 || k16 > 0) ? 1u : 0u);
+                    }
+                    tc_commit(&ax_empty[as]);   // frees the A and x stage once the MMAs above have read them
+                    if (++as == C::AS) {
+                        as = 0;
+                        ph ^= 1u;
+                    }
+                }
+                tc_commit(&acc_full[acc]);
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_ph ^= 1u;
+                }
+            }
+        }
+    } else if (warp < kTcWarpEpi0) {
+        // ---------------- dequant: raw int4 blocks -> fp16 A operand (K-major, 128-byte swizzle) ----------------
+        const int dw = warp - kTcWarpDq0;
+        const int blk_i = dw >> 1, tt = dw & 1;
+        const int g = lane >> 2, t = lane & 3;
+        // rows tt*16 + g and + 8 of block blk_i; 16-byte chunk index inside the 128-k group: kc = 4 t + j
+        const int r_lo = blk_i * 32 + tt * 16 + g;
+        const uint32_t row_off_lo = (uint32_t)(r_lo >> 3) * 1024u + (uint32_t)(r_lo & 7) * 128u;
+        const uint32_t row_off_hi = row_off_lo + 1024u;   // row + 8: next 8-row group, same row-in-group
+        const uint32_t ka_off = (uint32_t)(t >> 1) * (kTcRows * 128);
+        const int c_base = (t & 1) * 4;
+        int rs = 0, as = 0;
+        uint32_t rph = 0, aph = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            const int split = it % S;
+            const int g0 = (split * G) / S, g1 = ((split + 1) * G) / S;
+            for (int gi = g0; gi < g1; ++gi) {
+                mbar_wait_wd(&raw_full[rs], rph, p.err, 0x600 + rs);
+                const uint8_t* blk = smem + C::kRawOff + rs * kTcRawStage + blk_i * kW4BlockBytes;
+                const uint4 w0 = *reinterpret_cast<const uint4*>(blk + ((tt * 2 + 0) * 32 + lane) * 16);
+                const uint4 w1 = *reinterpret_cast<const uint4*>(blk + ((tt * 2 + 1) * 32 + lane) * 16);
+                const __half2 sc = *reinterpret_cast<const __half2*>(blk + kW4ScaleOff + (tt * 8 + g) * 4);
+                const int zz = blk[kW4ZeroOff + tt * 8 + g];
+                mbar_arrive(&raw_empty[rs]);
+                if (++rs == C::RS) {
+                    rs = 0;
+                    rph ^= 1u;
+                }
+                const __half2 c_lo = __float2half2_rn((float)(1024 + (zz & 0xF)));
+                const __half2 c_hi = __float2half2_rn((float)(64 + (zz >> 4)));
+                const __half2 s_lo = __half2half2(__low2half(sc)), s_hi = __half2half2(__high2half(sc));
+                mbar_wait_wd(&ax_empty[as], aph ^ 1u, p.err, 0x700 + as);
+                uint8_t* a_st = smem + C::kAOff + as * kTcAStage + ka_off;
+                const uint32_t words[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {   // k-step j: words 2j (k + 0..3) and 2j + 1 (k + 4..7)
+                    uint32_t lo0[2], hi0[2], lo1[2], hi1[2];
+                    tc_dequant_word(words[2 * j], c_lo, s_lo, c_hi, s_hi, lo0, hi0);
+                    tc_dequant_word(words[2 * j + 1], c_lo, s_lo, c_hi, s_hi, lo1, hi1);
+                    const uint32_t chunk = (uint32_t)(((c_base + j) ^ g) << 4);   // swizzle: chunk ^ (row % 8)
+                    *reinterpret_cast<uint4*>(a_st + row_off_lo + chunk) = make_uint4(lo0[0], lo0[1], lo1[0], lo1[1]);
+                    *reinterpret_cast<uint4*>(a_st + row_off_hi + chunk) = make_uint4(hi0[0], hi0[1], hi1[0], hi1[1]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor core
+                mbar_arrive(&a_full[as]);
+                if (++as == C::AS) {
+                    as = 0;
+                    aph ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ---------------- epilogue: TMEM -> registers -> global ----------------
+        const int q = warp & 3;                  // TMEM lane quadrant this warp may read
+        const int m = q * 32 + lane;             // row inside the tile
+        const int et = (warp - kTcWarpEpi0) * 32 + lane;
+        pdl_wait();
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            const int tile = it / S, split = it % S;
+            const int prow = tile * kTcRows + m;
+            mbar_wait_wd(&acc_full[acc], acc_ph, p.err, 0x800 + acc);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NTOK);
+            float* wsp = (S > 1) ? p.ws + ((size_t)(tile * S + split) * p.M) * kTcRows + m : nullptr;
+#pragma unroll 1
+            for (int c0 = 0; c0 < NTOK; c0 += 16) {
+                if (c0 >= p.M) break;
+                float v[16];
+                tc_ld16(taddr + (uint32_t)c0, v);
+                if (S > 1) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < p.M) __stcg(wsp + (size_t)(c0 + i) * kTcRows, v[i]);
+                } else {
+                    tc_epilogue16(p, prow, lane, c0, v);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[acc]);
+            if (++acc == 2) {
+                acc = 0;
+                acc_ph ^= 1u;
+            }
+            if (S > 1) {
+                // the last CTA of the tile reduces the S partial sums in split order and runs the epilogue
+                __threadfence();
+                epi_bar();
+                if (et == 0) *s_last = (atomicAdd(&p.counters[tile], 1u) == (unsigned)(S - 1)) ? 1u : 0u;
+                epi_bar();
+                const bool last = *s_last != 0u;
+                epi_bar();   // s_last may be rewritten by the next item
+                if (last) {
+                    __threadfence();
+                    const float* base = p.ws + ((size_t)tile * S * p.M) * kTcRows + m;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < p.M; c0 += 16) {
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                        for (int s = 0; s < S; ++s) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (c0 + i < p.M) v[i] += __ldcg(base + ((size_t)s * p.M + c0 + i) * kTcRows);
+                        }
+                        tc_epilogue16(p, prow, lane, c0, v);
+                    }
+                    if (et == 0) p.counters[tile] = 0u;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kTcWarpMma) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols));
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn tc_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+struct TcDeviceState {
+    float* ws = nullptr;
+    unsigned* counters = nullptr;
+    unsigned* err = nullptr;
+    size_t ws_bytes = 0;
+};
+static TcDeviceState g_tc_state[64];
+constexpr size_t kTcWsBytes = 64ull << 20;   // >= 2 x 148 items x 256 tokens x 128 rows x 4 B
+constexpr int kTcMaxTiles = 8192;
+
+static TcDeviceState* tc_state() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < 64) ? &g_tc_state[dev] : nullptr;
+}
+
+// allocates the per-device split-k workspace and sets the opt-in shared-memory sizes; must run outside stream capture
+cudaError_t prepare_w4_tc() {
+    TcDeviceState* st = tc_state();
+    if (!st) return cudaErrorInvalidDevice;
+    cudaError_t e;
+    if (!st->ws) {
+        if ((e = cudaMalloc((void**)&st->ws, kTcWsBytes)) != cudaSuccess) return e;
+        if ((e = cudaMalloc((void**)&st->counters, (kTcMaxTiles + 16) * sizeof(unsigned))) != cudaSuccess) return e;
+        if ((e = cudaMemset(st->counters, 0, (kTcMaxTiles + 16) * sizeof(unsigned))) != cudaSuccess) return e;
+        st->err = st->counters + kTcMaxTiles;
+        st->ws_bytes = kTcWsBytes;
+    }
+#define ZL_TC_SET(NT)                                                                                             \
+    if ((e = cudaFuncSetAttribute(k_w4a16_tc<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
+                                  TcCfg<NT>::kBytes)) != cudaSuccess)                                              \
+        return e;
+    ZL_TC_SET(32) ZL_TC_SET(64) ZL_TC_SET(128) ZL_TC_SET(256)
+#undef ZL_TC_SET
+    return cudaSuccess;
+}
+
+bool w4_tc_supports(int mc, int N, int K) {
+    return mc >= 1 && mc <= 256 && N % kTcRows == 0 && K % kW4GroupK == 0 && N / kTcRows <= kTcMaxTiles;
+}
+
+// k-split: fill the SMs when there are fewer row tiles than SMs (or an awkward number of waves), never below 4 groups
+// per item; every extra split costs an fp32 round trip of the (M x 128) partial tile through L2
+static int tc_pick_splits(int n_tiles, int G, int mc, size_t ws_bytes) {
+    const int sms = device_sm_count();
+    int best = 1;
+    float best_score = -1.f;
+    for (int s = 1; s <= 8 && s * 4 <= G; ++s) {
+        const long long items = (long long)n_tiles * s;
+        if (s > 1 && (size_t)items * mc * kTcRows * 4 > ws_bytes) break;
+        const long long waves = (items + sms - 1) / sms;
+        const float eff = (float)items / (float)(waves * sms);
+        const float score = eff - 0.03f * (s - 1);
+        if (score > best_score + 1e-6f) {
+            best_score = score;
+            best = s;
+        }
+    }
+    return best;
+}
+
+// last watchdog code published by a tcgen05 kernel on this device (0 = none); debugging aid
+extern "C" unsigned zl_w4_tc_watchdog(void) {
+    TcDeviceState* st = tc_state();
+    unsigned v = 0;
+    if (st && st->err) cudaMemcpy(&v, st->err, 4, cudaMemcpyDeviceToHost);
+    return v;
+}
+
+// k-split override: ZL_TC_SPLITS in the environment, or zl_w4_tc_set_splits (tests exercise the split-k reduction on
+// small shapes); 0 = automatic
+static int g_tc_splits = -2;
+static int tc_force_splits() {
+    if (g_tc_splits == -2) {
+        const char* e = getenv("ZL_TC_SPLITS");
+        g_tc_splits = e ? atoi(e) : 0;
+    }
+    return g_tc_splits;
+}
+extern "C" int zl_w4_tc_set_splits(int splits) {
+    g_tc_splits = splits < 0 ? 0 : splits;
+    return ZL_OK;
+}
+
+cudaError_t launch_w4_tc(const W4Params& p, bool pdl, cudaStream_t stream) {
+    TcDeviceState* st = tc_state();
+    EncodeTiledFn enc = tc_encode_fn();
+    if (!st || !st->ws || !enc) return cudaErrorNotSupported;
+    const int ntok = p.mc <= 32 ? 32 : p.mc <= 64 ? 64 : p.mc <= 128 ? 128 : 256;
+    W4TcParams q;
+    const cuuint64_t gdim[2] = {(cuuint64_t)p.K, (cuuint64_t)p.mc};
+    const cuuint64_t gstride[1] = {(cuuint64_t)p.ldx * 2};
+    const cuuint32_t box[2] = {64u, (cuuint32_t)ntok};
+    const cuuint32_t estr[2] = {1u, 1u};
+    if (enc(&q.xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(p.x), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return cudaErrorInvalidValue;
+    q.packed = p.packed;
+    q.bias = p.bias;
+    q.residual = p.residual;
+    q.y = p.y;
+    q.M = p.mc;
+    q.N = p.N;
+    q.K = p.K;
+    q.epi = p.epi;
+    const int n_tiles = p.N / kTcRows, G = p.K / kW4GroupK;
+    const int forced = tc_force_splits();
+    q.S = (forced > 0 && forced <= G) ? forced : tc_pick_splits(n_tiles, G, p.mc, st->ws_bytes);
+    if (q.S > 1 && (size_t)n_tiles * q.S * p.mc * kTcRows * 4 > st->ws_bytes) q.S = 1;
+    q.ws = st->ws;
+    q.counters = st->counters;
+    q.err = st->err;
+    q.cos = p.cos;
+    q.sin = p.sin;
+    q.q_out = p.q_out;
+    q.token_batch = p.token_batch;
+    q.placement = p.placement;
+    q.k_addrs = p.k_addrs;
+    q.v_addrs = p.v_addrs;
+    q.num_heads = p.num_heads;
+    q.num_kv_heads = p.num_kv_heads;
+    q.dim_head = p.dim_head;
+    const int items = n_tiles * q.S;
+    const int sms = device_sm_count();
+    const dim3 grid(items < sms ? items : sms), block(kTcThreads);
+    switch (ntok) {
+        case 32: return launch(k_w4a16_tc<32>, grid, block, (size_t)TcCfg<32>::kBytes, stream, pdl, q);
+        case 64: return launch(k_w4a16_tc<64>, grid, block, (size_t)TcCfg<64>::kBytes, stream, pdl, q);
+        case 128: return launch(k_w4a16_tc<128>, grid, block, (size_t)TcCfg<128>::kBytes, stream, pdl, q);
+        default: return launch(k_w4a16_tc<256>, grid, block, (size_t)TcCfg<256>::kBytes, stream, pdl, q);
+    }
+}
+
+}  // namespace zl
