@@ -113,7 +113,15 @@ int zl_w4a16_gemm(const void* x, int ldx, const void* packed, const void* bias, 
  *   epilogue ZL_EPI_QKV_ROPE: W is the fused qkv weight packed with zl_qkv_rope_row_map; the epilogue applies
  *                       rope_qk_cache (rotary_embedding_fuse_cache.cu:23-63) and copy_to_rag_buffer2
  *                       (ragged_buffer_kernel.cu:194-222, BSHD) and writes q (M, num_heads*dim_head).
+ *   tp_mode (tensor parallel, integer kernel only; replaces ModelContext::reduce_sum + element_add_scale between a
+ *                       row-parallel Linear and the next column-parallel one, model_context.cpp:203-243, block.cpp:123-141):
+ *                       2 on the row-parallel GEMM (o_proj / w_out, epilogue NONE, y unused): the fp16 partial tile is
+ *                       stored straight into every rank's NVLink-mapped inbox of tp_comm and the epoch flags are published;
+ *                       1 on the next GEMM: its activation row becomes T(T(sum_r partial_r) + x), x = residual stream,
+ *                       reduced in rank order while the activations are staged; the sum is also stored to tp_h_out
+ *                       (M, K; must not alias x).  0: off.
  * bias is indexed by PACKED row. */
+typedef struct zl_comm zl_comm_t;
 typedef struct zl_w4_fused_args {
     const void* x; int ldx; const void* packed; const void* bias; const void* residual; void* y;
     int M, N, K, group_size, epilogue, pdl;
@@ -123,6 +131,7 @@ typedef struct zl_w4_fused_args {
     int num_heads, num_kv_heads, dim_head;
     const void* prefetch_ptr; size_t prefetch_bytes; /* next kernel's weights: pulled into L2 as this one drains (may be NULL) */
     int variant; /* layout of `packed`: 0 ZLW4, 1 ZLW4I (integer kernel; needs the staged activations to fit smem) */
+    zl_comm_t* tp_comm; int tp_mode; void* tp_h_out;
 } zl_w4_fused_args_t;
 int zl_w4a16_gemm_fused(const zl_w4_fused_args_t* args, zl_stream_t stream);
 /* 1 if the exact-integer kernel (variant 1, M <= 16) can run this shape: its staged activations must fit shared memory. */
@@ -257,7 +266,6 @@ int zl_fill_uniform(void* p, size_t n, float lo, float hi, uint64_t seed, int dt
  * Replaces ModelContext::reduce_sum / reduce_sum2 / reduce_tp_int8 (src/model/model_context.cpp:203-326) and
  * the c10d NCCL wrappers it calls (3rd/bmengine/bmengine/c10d/c10d.cpp:42-136) on the decode path.
  * ------------------------------------------------------------------------------------------ */
-typedef struct zl_comm zl_comm_t;
 /* Allocates this rank's symmetric buffer (inboxes for world_size sources x 2 parities of max_elems 16-bit values). */
 int zl_comm_create(int rank, int world_size, size_t max_elems_16bit, zl_comm_t** out);
 void zl_comm_destroy(zl_comm_t* c);

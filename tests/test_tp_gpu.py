@@ -57,8 +57,15 @@ def _worker(rank, ws, port, q):
         dist.all_reduce(t)
         res["vs_nccl"] = float(rel_l2(out.float().cpu().numpy() - resid.astype(np.float32), t.float().cpu().numpy()))
 
-        # TP decode vs the single-GPU oracle
-        for quant in (5, 0):
+        # TP decode vs the single-GPU oracle.  W4 decode rides the exchange inside the GEMMs (partial tiles pushed into the
+        # peers' inboxes from the o_proj / w_out epilogues, reduced in the next GEMM's staging); ZL_TP_UNFUSED=1 keeps the
+        # stand-alone one-shot kernels: same arithmetic in the same order, so the two must agree bit for bit.
+        fused_logits = {}
+        for quant, unfused in ((5, False), (5, True), (0, False)):
+            if unfused:
+                os.environ["ZL_TP_UNFUSED"] = "1"
+            else:
+                os.environ.pop("ZL_TP_UNFUSED", None)
             sd = omodel.make_state_dict(TINY, quant, 128, False, seed=2)
             dec = LlamaDecoder(quant_type=quant, max_batch=2, max_seq=32, tp_rank=rank, tp_size=ws, **TINY)
             c2 = zdist.TPComm(2 * TINY["dim_model"], rank, ws)
@@ -68,7 +75,8 @@ def _worker(rank, ws, port, q):
             tok = np.array([5, 99], dtype=np.int32)
             worst = 0.0
             agree = True
-            for step in range(4):
+            same = True
+            for step in range(6):
                 pos = np.full(2, step, dtype=np.int32)
                 nxt, logits = dec.decode(tok, pos, want_logits=True)       # logits: this rank's vocab shard
                 ref = orc.decode(tok, pos)
@@ -78,10 +86,22 @@ def _worker(rank, ws, port, q):
                 for b in range(2):
                     if ref[b, order[b, -1]] - ref[b, order[b, -2]] > 2e-2:
                         agree = agree and nxt[b] == order[b, -1]
+                if quant == 5 and not unfused:
+                    fused_logits[step] = logits.copy()
+                if quant == 5 and unfused:
+                    same = same and np.array_equal(logits, fused_logits[step])
                 tok = nxt
-            res["tp_quant%d" % quant] = (float(worst), bool(agree))
+            kern = dec.stats(2)[1]
+            if quant == 5 and unfused:
+                res["tp_fused_equals_unfused"] = bool(same)
+                res["kernels_unfused"] = int(kern)
+            else:
+                res["tp_quant%d" % quant] = (float(worst), bool(agree))
+                if quant == 5:
+                    res["kernels_fused"] = int(kern)
             dec.close()
             c2.close()
+        os.environ.pop("ZL_TP_UNFUSED", None)
         # TP chunked prefill: with tp_size > 1 the two-half / two-stream pipeline is on by default --
         # the reduce stream all-reduces one half's partial sums while the compute stream runs the other half
         sd = omodel.make_state_dict(TINY, 5, 128, False, seed=4)
@@ -133,4 +153,6 @@ def test_tp_exchange_and_decode(lib, cuda, ws):
         assert res["vs_nccl"] < 2e-3, res
         assert res["tp_quant5"][0] < 3e-3 and res["tp_quant5"][1], res
         assert res["tp_quant0"][0] < 3e-3 and res["tp_quant0"][1], res
+        assert res["tp_fused_equals_unfused"], res
+        assert res["kernels_fused"] < res["kernels_unfused"], res        # 2 * layers - 1 exchange kernels are gone
         assert res["tp_prefill"] < 5e-3 and res["tp_prefill_then_decode"] < 5e-3, res

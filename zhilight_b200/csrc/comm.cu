@@ -12,39 +12,14 @@
 // The stand-alone group-32 int8 kernels of the reference (src/nn/quant/int8/quant_reduce_kernel.cu:14-38, 105-140,
 // 201-274) are provided bit-exactly at the end of this file.
 #include "common.cuh"
+#include "comm_dev.cuh"
 
 #include <cstring>
 #include <vector>
 
 namespace zl {
 
-constexpr int kCommMaxRanks = 8;
-constexpr int kCommMaxCtas = 64;         // <= #SMs so that every CTA of the kernel is resident (peers wait on peers)
 constexpr int kCommThreads = 256;
-
-struct CommDev {                        // lives in device memory (one copy per rank)
-    uint8_t* inbox[kCommMaxRanks];      // inbox[r] = base of rank r's symmetric buffer as mapped HERE
-    int rank, ws;
-    size_t slot_bytes;                  // bytes of one (parity, source-rank) slot
-    unsigned long long* epoch;          // local: number of completed exchanges
-    unsigned int* done;                 // local: CTAs finished in the current exchange
-};
-
-// layout of a rank's symmetric buffer:
-//   [2 parities][ws sources][slot_bytes payload]  then  flags [ws sources][kCommMaxCtas] (uint64, monotonic epochs)
-__host__ __device__ inline size_t comm_flags_offset(int ws, size_t slot_bytes) { return 2 * (size_t)ws * slot_bytes; }
-__host__ __device__ inline size_t comm_total_bytes(int ws, size_t slot_bytes) {
-    return comm_flags_offset(ws, slot_bytes) + (size_t)ws * kCommMaxCtas * sizeof(unsigned long long);
-}
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 
 // One-shot all-reduce of `n` elements (n % 8 == 0 for 16-bit payload; n % 32 == 0 for int8 payload).
 //   out = T( T(sum_r partial_r) + residual )   (residual may be null; out may alias residual)
@@ -334,6 +309,8 @@ extern "C" void zl_comm_destroy(zl_comm_t* c) {
 }
 
 extern "C" int zl_comm_rank(zl_comm_t* c) { return c ? c->rank : -1; }
+extern "C" const void* zl_comm_device_state(zl_comm_t* c) { return (c && c->opened) ? c->dev : nullptr; }
+extern "C" size_t zl_comm_slot_bytes(zl_comm_t* c) { return c ? c->slot_bytes : 0; }
 extern "C" int zl_comm_world_size(zl_comm_t* c) { return c ? c->ws : -1; }
 
 extern "C" int zl_allreduce_one_shot(zl_comm_t* c, const void* partial, const void* residual, void* out, size_t n,

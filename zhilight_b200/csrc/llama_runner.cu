@@ -8,10 +8,12 @@
 // CUDA graph per batch size.
 #include "common.cuh"
 #include "w4_layout.cuh"
+#include "comm_dev.cuh"
 
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -66,6 +68,7 @@ struct zl_llama {
     // local (per-rank) sizes
     int hq = 0, hkv = 0, ff = 0;
     // activations
+    void* h2 = nullptr;   // second residual-stream buffer: the fused TP exchange ping-pongs between h and h2
     void *h = nullptr, *xn = nullptr, *qkv = nullptr, *q = nullptr, *ao = nullptr, *act = nullptr,
          *pend = nullptr, *gu = nullptr;
     float* logits = nullptr;
@@ -560,6 +563,7 @@ int alloc_runtime(zl_llama* m) {
     m->tok_cap = T;
     RCHECK(dmalloc(&m->h, (size_t)T * D * 2));
     RCHECK(dmalloc(&m->xn, (size_t)T * D * 2));
+    if (c.tp_size > 1) RCHECK(dmalloc(&m->h2, (size_t)T * D * 2));
     RCHECK(dmalloc(&m->pend, (size_t)T * D * 2));
     RCHECK(dmalloc(&m->qkv, (size_t)T * (m->hq + 2 * m->hkv) * d * 2));
     RCHECK(dmalloc(&m->q, (size_t)T * m->hq * d * 2));
@@ -659,7 +663,8 @@ static int no_pdl_mask() {
 }
 
 int w4_gemm(zl_llama* m, const void* x, int ldx, const W4Lin& w, const void* residual, void* y, int B, int epi,
-            const void* ln_w, const Layer* rope_layer, int layer = -1, int slot = -1, int row0 = 0, int force_no_pdl = 0) {
+            const void* ln_w, const Layer* rope_layer, int layer = -1, int slot = -1, int row0 = 0, int force_no_pdl = 0,
+            int tp_mode = 0, void* tp_h_out = nullptr) {
     const auto& c = m->cfg;
     zl_w4_fused_args_t a = {};
     a.x = x;
@@ -714,6 +719,11 @@ int w4_gemm(zl_llama* m, const void* x, int ldx, const W4Lin& w, const void* res
         a.dim_head = c.dim_head;
     }
     if (force_no_pdl) a.pdl = 0;
+    if (tp_mode) {
+        a.tp_comm = m->comm;
+        a.tp_mode = tp_mode;
+        a.tp_h_out = tp_h_out;
+    }
     return zl_w4a16_gemm_fused(&a, m->stream);
 }
 
@@ -870,22 +880,42 @@ int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* p
     RCHECK(zl_embedding(m->cur_tokens, m->emb, m->h, B, D, c.vocab_size, dt, 0, st));
     const bool dual = pf && prefill_dual_enabled(m, pf->n);
     if (dual) RCHECK(prefill_layers_dual(m, *pf));
+    // Tensor parallel, decode-sized launches of a W4 model: the exchange rides inside the GEMMs.  The row-parallel GEMMs
+    // (o_proj, w_out) push their fp16 partial tiles into every rank's inbox from the epilogue; the next GEMM (gate_up, next
+    // layer's qkv) reduces them in rank order while it stages its activations and writes the new residual stream to the
+    // other of the two buffers h / h2.  Only the last layer's w_out keeps the stand-alone one-shot kernel (the final norm
+    // is not a GEMM).  ZL_TP_UNFUSED=1 keeps the separate exchange kernels everywhere (A/B).
+    bool tp_fused = tp && w4 && !pf && c.fuse >= 1 && !c.tp_int8 && dt == ZL_F16 && !getenv("ZL_TP_UNFUSED") && !skip &&
+                    (size_t)B * D * 2 <= zl_comm_slot_bytes(m->comm);
+    if (tp_fused) {
+        const Layer& L0 = m->layers[0];
+        for (const W4Lin* w : {&L0.q_qkv, &L0.q_o, &L0.q_gu, &L0.q_down})
+            if (!w->packed_i || zl_w4_int_layout_route(B, w->N, w->K) != 3) tp_fused = false;
+    }
+    void* hc = m->h;    // current residual stream
+    void* ho = m->h2;   // where the next fused reduce-in writes it
+    bool pending = false;   // partial sums of the previous row-parallel GEMM are in flight to the inboxes
     for (int l = 0; l < (dual ? 0 : c.num_layers); ++l) {
         Layer& L = m->layers[l];
         if (w4) {
             const void* xin = m->xn;
             const void* lnw = nullptr;
             if (c.fuse >= 1) {
-                xin = m->h;
+                xin = hc;
                 lnw = L.ln_attn;
             } else {
-                RCHECK(zl_rmsnorm(m->h, L.ln_attn, m->xn, B, D, c.eps, 1.f, dt, pdl, st));
+                RCHECK(zl_rmsnorm(hc, L.ln_attn, m->xn, B, D, c.eps, 1.f, dt, pdl, st));
             }
+            const int tpm = pending ? 1 : 0;
             if (skip & 2) {
             } else if (c.fuse >= 2) {
-                RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, nullptr, B, ZL_EPI_QKV_ROPE, lnw, &L, l, 0));
+                RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, nullptr, B, ZL_EPI_QKV_ROPE, lnw, &L, l, 0, 0, 0, tpm, ho));
             } else {
-                RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, m->qkv, B, ZL_EPI_NONE, lnw, nullptr, l, 0));
+                RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, m->qkv, B, ZL_EPI_NONE, lnw, nullptr, l, 0, 0, 0, tpm, ho));
+            }
+            if (pending) {
+                std::swap(hc, ho);
+                pending = false;
             }
         } else {
             // residual of the previous layer's FFN is folded into this norm (block.cpp:139-141 + 131)
@@ -912,28 +942,39 @@ int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* p
                                        m->hq, m->hkv, d, 1, m->attn_ws, m->attn_ws_bytes, dt, P(2), st));
         if (w4) {
             if (skip & 4) {
+            } else if (tp_fused) {
+                RCHECK(w4_gemm(m, m->ao, m->hq * d, L.q_o, nullptr, nullptr, B, ZL_EPI_NONE, nullptr, nullptr, l, 2, 0, 0, 2));
+                pending = true;
             } else if (tp) {
                 // row-parallel: partial sums -> one-shot NVLink all-reduce fused with the residual add
                 RCHECK(w4_gemm(m, m->ao, m->hq * d, L.q_o, nullptr, m->pend, B, ZL_EPI_NONE, nullptr, nullptr, l, 2));
-                RCHECK(zl_allreduce_one_shot(m->comm, m->pend, m->h, m->h, (size_t)B * D, dt, c.tp_int8, pdl, st));
+                RCHECK(zl_allreduce_one_shot(m->comm, m->pend, hc, hc, (size_t)B * D, dt, c.tp_int8, pdl, st));
             } else {
-                RCHECK(w4_gemm(m, m->ao, m->hq * d, L.q_o, m->h, m->h, B, ZL_EPI_RESIDUAL, nullptr, nullptr, l, 2));
+                RCHECK(w4_gemm(m, m->ao, m->hq * d, L.q_o, hc, hc, B, ZL_EPI_RESIDUAL, nullptr, nullptr, l, 2));
             }
             const void* xin = m->xn;
             const void* lnw = nullptr;
             if (c.fuse >= 1) {
-                xin = m->h;
+                xin = hc;
                 lnw = L.ln_ff;
             } else {
-                RCHECK(zl_rmsnorm(m->h, L.ln_ff, m->xn, B, D, c.eps, 1.f, dt, pdl, st));
+                RCHECK(zl_rmsnorm(hc, L.ln_ff, m->xn, B, D, c.eps, 1.f, dt, pdl, st));
             }
-            if (!(skip & 8)) RCHECK(w4_gemm(m, xin, D, L.q_gu, nullptr, m->act, B, ZL_EPI_SWIGLU, lnw, nullptr, l, 3));
+            if (!(skip & 8))
+                RCHECK(w4_gemm(m, xin, D, L.q_gu, nullptr, m->act, B, ZL_EPI_SWIGLU, lnw, nullptr, l, 3, 0, 0, pending ? 1 : 0, ho));
+            if (pending) {
+                std::swap(hc, ho);
+                pending = false;
+            }
             if (skip & 16) {
+            } else if (tp_fused && l + 1 < c.num_layers) {
+                RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, nullptr, nullptr, B, ZL_EPI_NONE, nullptr, nullptr, l, 4, 0, 0, 2));
+                pending = true;
             } else if (tp) {
                 RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, nullptr, m->pend, B, ZL_EPI_NONE, nullptr, nullptr, l, 4));
-                RCHECK(zl_allreduce_one_shot(m->comm, m->pend, m->h, m->h, (size_t)B * D, dt, c.tp_int8, pdl, st));
+                RCHECK(zl_allreduce_one_shot(m->comm, m->pend, hc, hc, (size_t)B * D, dt, c.tp_int8, pdl, st));
             } else {
-                RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, m->h, m->h, B, ZL_EPI_RESIDUAL, nullptr, nullptr, l, 4));
+                RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, hc, hc, B, ZL_EPI_RESIDUAL, nullptr, nullptr, l, 4));
             }
         } else {
             RCHECK(dense_or_w8(m, m->ao, L.d_o, m->pend, B, pdl));
@@ -957,7 +998,7 @@ int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* p
                                   1.f, 0, dt, pdl, st));
         }
     } else if (w4) {
-        RCHECK(zl_rmsnorm(m->h, m->ln_f, m->xn, B, D, c.eps, 1.f, dt, P(32), st));
+        RCHECK(zl_rmsnorm(hc, m->ln_f, m->xn, B, D, c.eps, 1.f, dt, P(32), st));
     } else {
         RCHECK(zl_add_rmsnorm(m->h, m->pend, m->ln_f, m->h, m->xn, B, D, c.eps, 1.f, 0, dt, P(32), st));
     }
@@ -1076,7 +1117,7 @@ extern "C" void zl_llama_destroy(zl_llama_t* m) {
     }
     for (void* p : {m->emb, m->lm_head_tied ? nullptr : m->lm_head, m->ln_f, m->h, m->xn, m->qkv, m->q, m->ao, m->act,
                     m->pend, m->gu, (void*)m->logits, (void*)m->cosb, (void*)m->sinb, (void*)m->d_tokens,
-                    (void*)m->d_pos, (void*)m->d_lens, (void*)m->d_next, (void*)m->d_iota, m->attn_ws, m->argmax_ws, (void*)m->d_tb, (void*)m->d_mask, m->xq, (void*)m->xs})
+                    m->h2, (void*)m->d_pos, (void*)m->d_lens, (void*)m->d_next, (void*)m->d_iota, m->attn_ws, m->argmax_ws, (void*)m->d_tb, (void*)m->d_mask, m->xq, (void*)m->xs})
         if (p) cudaFree(p);
     if (m->reduce_stream) {
         cudaStreamSynchronize(m->reduce_stream);

@@ -31,6 +31,13 @@ struct W4Params {
     unsigned long long pf_bytes;
     unsigned long long* trace;   // debug: per-CTA globaltimer samples [grid][16] (zl_w4_set_trace)
     int dbg;   // ZL_W4_DEBUG: 1 = skip dequant/MMA (pure weight-stream probe; results are garbage)
+    // tensor-parallel exchange inside the GEMM (integer kernel only; comm_dev.cuh).  tp_mode 1 (reduce-in): the
+    // activation row is  T(T(sum over ranks of the partial sums pushed by the previous row-parallel GEMM) + x)  -- x is the
+    // residual stream -- and CTA 0 stores it to tp_h_out (must not alias x).  tp_mode 2 (push): the epilogue stores the
+    // fp16 partial tile into every rank's inbox and the last CTA publishes the epoch flags.
+    const void* tp_cd = nullptr;   // const CommDev*
+    int tp_mode = 0;
+    __half* tp_h_out = nullptr;
 };
 
 cudaError_t launch_w4_v2(const W4Params& p, bool pdl, cudaStream_t stream);

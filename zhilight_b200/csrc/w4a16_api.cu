@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "w4_layout.cuh"
 #include "w4_params.h"
+#include "comm_dev.cuh"
 
 #include <cstdlib>
 
@@ -104,13 +105,31 @@ extern "C" int zl_w4a16_gemm_fused(const zl_w4_fused_args_t* a, zl_stream_t stre
     ZL_CHECK_ARG(a->epilogue >= ZL_EPI_NONE && a->epilogue <= ZL_EPI_QKV_ROPE);
     ZL_CHECK_ARG(a->variant == kW4VariantHalf || a->variant == kW4VariantInt);
     ZL_CHECK_ARG(a->epilogue != ZL_EPI_RESIDUAL || a->residual != nullptr);
-    ZL_CHECK_ARG(a->epilogue == ZL_EPI_QKV_ROPE || a->y != nullptr);
+    ZL_CHECK_ARG(a->epilogue == ZL_EPI_QKV_ROPE || a->y != nullptr || a->tp_mode == 2);
     ZL_CHECK_ARG(a->ln_weight == nullptr || (reinterpret_cast<uintptr_t>(a->ln_weight) & 15) == 0);
     if (a->epilogue == ZL_EPI_QKV_ROPE) {
         ZL_CHECK_ARG(a->cos && a->sin && a->q_out && a->token_batch && a->placement && a->k_addrs && a->v_addrs);
         ZL_CHECK_ARG(a->num_heads > 0 && a->num_kv_heads > 0 && a->dim_head > 0);
         ZL_CHECK_SUPPORTED(a->dim_head % 32 == 0);
         ZL_CHECK_ARG(a->N == (a->num_heads + 2 * a->num_kv_heads) * a->dim_head);
+    }
+    const void* tp_cd = nullptr;
+    if (a->tp_mode != 0) {
+        ZL_CHECK_ARG(a->tp_mode == 1 || a->tp_mode == 2);
+        ZL_CHECK_ARG(a->tp_comm != nullptr && a->variant == kW4VariantInt);
+        tp_cd = zl_comm_device_state(a->tp_comm);
+        if (!tp_cd) {
+            zl_set_last_error(__FILE__, __LINE__, "tp_comm: peers not opened");
+            return ZL_ERR_STATE;
+        }
+        ZL_CHECK_SUPPORTED(a->M <= 16 && w4_v3_fits(a->M, a->N, a->K) && "tp_mode needs the integer kernel (M <= 16)");
+        if (a->tp_mode == 1) {
+            ZL_CHECK_ARG(a->tp_h_out != nullptr && a->tp_h_out != a->x && a->ldx == a->K);
+            ZL_CHECK_ARG((size_t)a->M * a->K * 2 <= zl_comm_slot_bytes(a->tp_comm));
+        } else {
+            ZL_CHECK_ARG(a->epilogue == ZL_EPI_NONE && a->bias == nullptr);
+            ZL_CHECK_ARG((size_t)a->M * a->N * 2 <= zl_comm_slot_bytes(a->tp_comm));
+        }
     }
     const int n_out = a->epilogue == ZL_EPI_SWIGLU ? a->N / 2 : a->N;
     // rows per pass: the tcgen05 kernel takes up to 256 tokens at once, the mma.sync kernels 32 (v2) / 16 (v3)
@@ -152,6 +171,9 @@ extern "C" int zl_w4a16_gemm_fused(const zl_w4_fused_args_t* a, zl_stream_t stre
         }
         p.trace = g_w4_trace;
         if (p.dbg & 32) p.ln_w = nullptr;   // timing probe: drop the fused RMSNorm (results are wrong)
+        p.tp_cd = tp_cd;
+        p.tp_mode = a->tp_mode;
+        p.tp_h_out = static_cast<__half*>(a->tp_h_out);
         p.pf_ptr = static_cast<const uint8_t*>(a->prefetch_ptr);
         p.pf_bytes = a->prefetch_bytes;
         if (route == 4) {

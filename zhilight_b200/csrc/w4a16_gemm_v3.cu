@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "w4_layout.cuh"
 #include "w4_params.h"
+#include "comm_dev.cuh"
 
 #include <cstdlib>
 
@@ -243,6 +244,27 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
     pdl_wait();   // everything above touched only constants; x / residual / KV come from predecessor kernels
     stamp();
 
+    // ---- tensor-parallel reduce-in: wait until every peer has pushed its partial sums of the previous row-parallel
+    // GEMM into this rank's inbox (flag[src][0] >= epoch; the local producer already advanced the epoch) ----
+    const CommDev* tp = static_cast<const CommDev*>(p.tp_cd);
+    const uint8_t* tp_slots = nullptr;   // [ws][slot_bytes] of the exchange's parity
+    size_t tp_slot_bytes = 0;
+    int tp_ws = 0;
+    if (p.tp_mode == 1) {
+        const unsigned long long ep = *reinterpret_cast<volatile unsigned long long*>(tp->epoch);
+        tp_ws = tp->ws;
+        tp_slot_bytes = tp->slot_bytes;
+        const uint8_t* mine = tp->inbox[tp->rank];
+        if ((int)threadIdx.x < tp_ws && (int)threadIdx.x != tp->rank) {
+            const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(mine + comm_flags_offset(tp_ws, tp_slot_bytes)) +
+                                             (size_t)threadIdx.x * kCommMaxCtas;
+            while (ld_acquire_sys(flag) < ep) {
+            }
+        }
+        tp_slots = mine + ((ep - 1ull) & 1ull) * (size_t)tp_ws * tp_slot_bytes;
+        __syncthreads();
+    }
+
     // ---- stage the activations as block-floating-point integers, once per CTA ----
     for (int tok = 0; tok < p.mc; ++tok) {
         uint2 raw[kMaxNg];
@@ -250,6 +272,47 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
         for (int gl = 0; gl < kMaxNg; ++gl) {
             const int gi = warp + gl * WT;
             if (gi < G) raw[gl] = ld_cg_u2(p.x + (size_t)tok * p.ldx + gi * kW4GroupK + lane * 4);
+        }
+        if (p.tp_mode == 1) {
+            // x := T(T(sum_r partial_r) + x): fp32 sum in rank order (identical on every rank and CTA), the reference's
+            // reduce_sum + element_add_scale rounding points (model_context.cpp:203-243, block_kernel.cu:7-17)
+            float acc[kMaxNg][4];
+#pragma unroll
+            for (int gl = 0; gl < kMaxNg; ++gl) acc[gl][0] = acc[gl][1] = acc[gl][2] = acc[gl][3] = 0.f;
+            for (int r = 0; r < tp_ws; ++r) {
+                const __half* src = reinterpret_cast<const __half*>(tp_slots + (size_t)r * tp_slot_bytes) + (size_t)tok * p.K;
+                uint2 t[kMaxNg];
+#pragma unroll
+                for (int gl = 0; gl < kMaxNg; ++gl) {
+                    const int gi = warp + gl * WT;
+                    if (gi < G) t[gl] = ld_cg_u2(src + gi * kW4GroupK + lane * 4);
+                }
+#pragma unroll
+                for (int gl = 0; gl < kMaxNg; ++gl) {
+                    const int gi = warp + gl * WT;
+                    if (gi < G) {
+                        const float2 a = __half22float2(*reinterpret_cast<__half2*>(&t[gl].x));
+                        const float2 b = __half22float2(*reinterpret_cast<__half2*>(&t[gl].y));
+                        acc[gl][0] += a.x;
+                        acc[gl][1] += a.y;
+                        acc[gl][2] += b.x;
+                        acc[gl][3] += b.y;
+                    }
+                }
+            }
+#pragma unroll
+            for (int gl = 0; gl < kMaxNg; ++gl) {
+                const int gi = warp + gl * WT;
+                if (gi < G) {
+                    const __half2 s01 = __floats2half2_rn(acc[gl][0], acc[gl][1]), s23 = __floats2half2_rn(acc[gl][2], acc[gl][3]);
+                    const __half2 h01 = __hadd2(s01, *reinterpret_cast<__half2*>(&raw[gl].x));
+                    const __half2 h23 = __hadd2(s23, *reinterpret_cast<__half2*>(&raw[gl].y));
+                    raw[gl].x = *reinterpret_cast<const uint32_t*>(&h01);
+                    raw[gl].y = *reinterpret_cast<const uint32_t*>(&h23);
+                    if (blockIdx.x == 0)
+                        *reinterpret_cast<uint2*>(p.tp_h_out + (size_t)tok * p.K + gi * kW4GroupK + lane * 4) = raw[gl];
+                }
+            }
         }
         float sq = 0.f;
         bool bad = false;
@@ -319,6 +382,16 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
     }
     __syncthreads();
     stamp();
+
+    // tensor-parallel push: slot (parity of the epoch, this rank) of every rank's inbox
+    int tp_push_ws = 0;
+    unsigned long long tp_epoch = 0;
+    size_t tp_my_slot = 0;
+    if (p.tp_mode == 2) {
+        tp_epoch = *reinterpret_cast<volatile unsigned long long*>(tp->epoch);
+        tp_push_ws = tp->ws;
+        tp_my_slot = ((size_t)(tp_epoch & 1ull) * tp->ws + tp->rank) * tp->slot_bytes;
+    }
 
     int c_slot = 0;
     uint32_t c_parity = 0;
@@ -563,6 +636,11 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
                 v += s_poison[tok];
                 if (p.bias) v += __half2float(p.bias[n0 + row]);
                 __half h = __float2half_rn(v);
+                if (p.tp_mode == 2) {   // partial sum of a row-parallel GEMM: straight into every rank's inbox (own slot too)
+                    for (int r = 0; r < tp_push_ws; ++r)
+                        reinterpret_cast<__half*>(tp->inbox[r] + tp_my_slot)[(size_t)tok * p.N + n0 + row] = h;
+                    continue;
+                }
                 if (p.epi == ZL_EPI_RESIDUAL)
                     h = __float2half_rn(__half2float(h) + __half2float(p.residual[(size_t)tok * p.N + n0 + row]));
                 p.y[(size_t)tok * p.N + n0 + row] = h;
@@ -570,6 +648,26 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
         }
         if (S::kRedBufs == 1) sub_barrier(1 + sub, WARPS * 32);
         stamp();
+    }
+    if (p.tp_mode == 2) {
+        // every store of this CTA is fenced to system scope, then the last CTA of the grid publishes the flags: the peers'
+        // next GEMM (reduce-in above) acquires them.  Advancing the local epoch tells the local consumer which exchange
+        // to wait for.
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (atomicAdd(tp->done, 1u) == gridDim.x - 1) {
+                *tp->done = 0;
+                __threadfence_system();
+                for (int r = 0; r < tp_push_ws; ++r)
+                    if (r != tp->rank)
+                        st_release_sys(reinterpret_cast<unsigned long long*>(tp->inbox[r] + comm_flags_offset(tp->ws, tp->slot_bytes)) +
+                                           (size_t)tp->rank * kCommMaxCtas,
+                                       tp_epoch + 1);
+                __threadfence();
+                *reinterpret_cast<volatile unsigned long long*>(tp->epoch) = tp_epoch + 1;
+            }
+        }
     }
 }
 
