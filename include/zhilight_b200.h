@@ -317,6 +317,8 @@ typedef struct zl_llama_config {
                * + qkv RoPE/KV-append epilogue.  Launches with more than 16 tokens run zl_rmsnorm + the tcgen05 GEMM. */
     int prefill_chunk; /* 0: decode only.  1..2048: zl_llama_prefill processes a prompt in chunks of this many tokens
                         * (chunked prefill, zhilight/config/adapter.py:47-48) */
+    int qkv_bias; /* zl_llama_init_synthetic: also create q/k/v biases (Qwen2: attention.cpp:105-109); loaded checkpoints
+                   * carry their ".bias" tensors regardless of this flag */
 } zl_llama_config_t;
 
 int zl_llama_create(const zl_llama_config_t* cfg, zl_llama_t** out);

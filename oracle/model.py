@@ -145,8 +145,9 @@ class OracleLlama:
         return np.asarray(xn, F32) @ _f32(lm, T).T
 
 
-def make_state_dict(cfg, quant_type=0, group_size=128, sym=False, seed=0, tied=False, dtype="f16"):
-    """Random checkpoint with ZhiLight names (zhilight/loader.py:250-358)."""
+def make_state_dict(cfg, quant_type=0, group_size=128, sym=False, seed=0, tied=False, dtype="f16", scale_range=None):
+    """Random checkpoint with ZhiLight names (zhilight/loader.py:250-358).  scale_range = (lo, hi) of the GPTQ group scales
+    (wide layers need small ones to keep fp16 activations finite)."""
     rng = np.random.default_rng(seed)
     c = cfg
     d_model, d = c["dim_model"], c["dim_head"]
@@ -160,7 +161,8 @@ def make_state_dict(cfg, quant_type=0, group_size=128, sym=False, seed=0, tied=F
 
     def linear(prefix, k, n, s):
         if quant_type == 5:
-            qw, qz, sc, gi = gptq.make_gptq_checkpoint(k, n, group_size, sym, s)
+            extra = {} if scale_range is None else dict(scale_lo=scale_range[0], scale_hi=scale_range[1])
+            qw, qz, sc, gi = gptq.make_gptq_checkpoint(k, n, group_size, sym, s, **extra)
             sd[prefix + ".qweight"], sd[prefix + ".qzeros"], sd[prefix + ".scales"] = qw, qz, sc
         elif quant_type == 6:
             r = np.random.default_rng(s)

@@ -228,3 +228,34 @@ def test_marlin_quant_type_is_served_by_the_gptq_kernels(lib, cuda):
         outs.append(logits.copy())
         dec.close()
     np.testing.assert_array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("cfg", [TINY, TINY128], ids=["d64", "d128"])
+def test_qkv_bias_model_matches_oracle(lib, cuda, cfg):
+    """Qwen2-style q/k/v biases (attention.cpp:105-109) through the fused qkv GEMM: the bias is gathered into packed-row
+    order at load and added before RoPE, like the reference's Linear bias."""
+    from zhilight_b200.llama import LlamaDecoder
+    sd = omodel.make_state_dict(cfg, 5, 128, False, seed=21)
+    rng = np.random.default_rng(5)
+    d = cfg["dim_head"]
+    for l in range(cfg["num_layers"]):
+        for name, n in (("project_q", cfg["num_heads"] * d), ("project_k", cfg["num_kv_heads"] * d),
+                        ("project_v", cfg["num_kv_heads"] * d)):
+            sd["layers.%d.attn.%s.bias" % (l, name)] = (0.5 * rng.standard_normal(n)).astype(np.float16)
+    orc = omodel.OracleLlama(cfg, sd, 5, 128, False, "f16", fuse_norm=True)
+    for fuse in (0, 2):
+        dec = LlamaDecoder(quant_type=5, max_batch=3, max_seq=64, fuse=fuse, **cfg)
+        dec.load_state_dict(sd)
+        o = omodel.OracleLlama(cfg, sd, 5, 128, False, "f16", fuse_norm=fuse >= 1)
+        tok = np.array([3, 17, 101], dtype=np.int32)
+        for step in range(4):
+            pos = np.full(3, step, dtype=np.int32)
+            nxt, logits = dec.decode(tok, pos, want_logits=True)
+            ref = o.decode(tok, pos)
+            assert rel_l2(logits, ref) <= 3e-3, (fuse, step)
+            tok = np.argmax(ref, axis=1).astype(np.int32)
+        dec.close()
+    # and the biases matter: without them the logits differ visibly
+    sd2 = {k: v for k, v in sd.items() if not k.endswith(".bias")}
+    ref_nobias = omodel.OracleLlama(cfg, sd2, 5, 128, False, "f16", fuse_norm=True).decode(np.array([3]), [0])
+    assert rel_l2(orc.decode(np.array([3]), [0]), ref_nobias) > 1e-2

@@ -1238,6 +1238,11 @@ extern "C" int zl_llama_init_synthetic(zl_llama_t* m, uint64_t seed) {
         RCHECK(stage_random_linear(m, p + "attn.project_q", D, m->hq * d, seed));
         RCHECK(stage_random_linear(m, p + "attn.project_k", D, m->hkv * d, seed));
         RCHECK(stage_random_linear(m, p + "attn.project_v", D, m->hkv * d, seed));
+        if (c.qkv_bias) {
+            RCHECK(stage_random(m, p + "attn.project_q.bias", 1, m->hq * d, 2, 2, -0.03f, 0.03f, seed));
+            RCHECK(stage_random(m, p + "attn.project_k.bias", 1, m->hkv * d, 2, 2, -0.03f, 0.03f, seed));
+            RCHECK(stage_random(m, p + "attn.project_v.bias", 1, m->hkv * d, 2, 2, -0.03f, 0.03f, seed));
+        }
         RCHECK(stage_random_linear(m, p + "attn.attn_out", m->hq * d, D, seed));
         RCHECK(stage_random_linear(m, p + "ff.w_in", D, m->ff, seed));
         RCHECK(stage_random_linear(m, p + "ff.w_gated", D, m->ff, seed));
@@ -1333,10 +1338,20 @@ extern "C" int zl_llama_bench_gemms(zl_llama_t* m, int B, int iters, float* ms, 
         for (int l = 0; l < c.num_layers; ++l) {
             Layer& L = m->layers[l];
             if (w4) {
-                RCHECK(w4_gemm(m, m->xn, D, L.q_qkv, nullptr, m->qkv, B, ZL_EPI_NONE, nullptr, nullptr));
-                RCHECK(w4_gemm(m, m->ao, m->hq * d, L.q_o, m->pend, m->pend, B, ZL_EPI_RESIDUAL, nullptr, nullptr));
-                RCHECK(w4_gemm(m, m->xn, D, L.q_gu, nullptr, m->act, B, ZL_EPI_SWIGLU, nullptr, nullptr));
-                RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, m->pend, m->pend, B, ZL_EPI_RESIDUAL, nullptr, nullptr));
+                // the SAME kernel variants as the decode step (enqueue_step): fused RMSNorm prologue, qkv RoPE + KV-append
+                // epilogue, SwiGLU, residual epilogues, per-kernel PDL policy.  (Rewrites the KV rows of the current
+                // positions and the residual stream: call it after the measurements that need the decode state.)
+                const void* ln1 = c.fuse >= 1 ? L.ln_attn : nullptr;
+                const void* ln2 = c.fuse >= 1 ? L.ln_ff : nullptr;
+                m->cur_tb = m->d_iota;
+                m->cur_pos = m->d_pos;
+                if (c.fuse >= 2)
+                    RCHECK(w4_gemm(m, m->h, D, L.q_qkv, nullptr, nullptr, B, ZL_EPI_QKV_ROPE, ln1, &L, l, 0));
+                else
+                    RCHECK(w4_gemm(m, ln1 ? m->h : m->xn, D, L.q_qkv, nullptr, m->qkv, B, ZL_EPI_NONE, ln1, nullptr, l, 0));
+                RCHECK(w4_gemm(m, m->ao, m->hq * d, L.q_o, m->h, m->h, B, ZL_EPI_RESIDUAL, nullptr, nullptr, l, 2));
+                RCHECK(w4_gemm(m, ln2 ? m->h : m->xn, D, L.q_gu, nullptr, m->act, B, ZL_EPI_SWIGLU, ln2, nullptr, l, 3));
+                RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, m->h, m->h, B, ZL_EPI_RESIDUAL, nullptr, nullptr, l, 4));
                 if (it == 0) {
                     nbytes += (double)zl_w4_packed_bytes(L.q_qkv.N, D, c.group_size) +
                               (double)zl_w4_packed_bytes(D, m->hq * d, c.group_size) +

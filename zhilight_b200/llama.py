@@ -19,6 +19,13 @@ MODEL_PRESETS = {
     "llama-3.2-1b": dict(num_layers=16, dim_model=2048, num_heads=32, num_kv_heads=8, dim_head=64, dim_ff=8192,
                          vocab_size=128256, eps=1e-5, rope_theta=500000.0,
                          rope_llama3=dict(factor=32.0, low=1.0, high=4.0, orig=8192.0)),
+    # north_star TP=8 target and BASELINE config 4 (Qwen2-72B GPTQ: FF padded to 29696 in the GPTQ build,
+    # zhilight/config/qwen2_adapter.py:27-28; q/k/v bias, attention.cpp:105-109)
+    "llama-3.1-70b": dict(num_layers=80, dim_model=8192, num_heads=64, num_kv_heads=8, dim_head=128, dim_ff=28672,
+                          vocab_size=128256, eps=1e-5, rope_theta=500000.0,
+                          rope_llama3=dict(factor=8.0, low=1.0, high=4.0, orig=8192.0)),
+    "qwen2-72b": dict(num_layers=80, dim_model=8192, num_heads=64, num_kv_heads=8, dim_head=128, dim_ff=29696,
+                      vocab_size=152064, eps=1e-6, rope_theta=1000000.0, rope_llama3=None, qkv_bias=True),
     "tiny": dict(num_layers=2, dim_model=256, num_heads=4, num_kv_heads=2, dim_head=64, dim_ff=512,
                  vocab_size=512, eps=1e-5, rope_theta=10000.0, rope_llama3=None),
 }
@@ -30,14 +37,14 @@ class LlamaDecoder:
     def __init__(self, num_layers, dim_model, num_heads, num_kv_heads, dim_head, dim_ff, vocab_size, eps=1e-5,
                  rope_theta=10000.0, rope_llama3=None, quant_type=QUANT_NONE, group_size=128, sym=False,
                  dtype="f16", max_batch=1, max_seq=512, use_pdl=True, use_graph=True, tp_rank=0, tp_size=1, fuse=2, tp_int8=False,
-                 prefill_chunk=0):
+                 prefill_chunk=0, qkv_bias=False):
         self.lib = _lib.load()
         l3 = rope_llama3 or {}
         self.cfg = _lib.LlamaConfig(
             num_layers, dim_model, num_heads, num_kv_heads, dim_head, dim_ff, vocab_size, eps, rope_theta,
             float(l3.get("factor", 0.0)), float(l3.get("low", 1.0)), float(l3.get("high", 4.0)),
             float(l3.get("orig", 8192.0)), quant_type, group_size, int(sym), {"f16": 0, "bf16": 1}[dtype],
-            max_batch, max_seq, tp_rank, tp_size, int(use_pdl), int(use_graph), int(tp_int8), int(fuse), int(prefill_chunk))
+            max_batch, max_seq, tp_rank, tp_size, int(use_pdl), int(use_graph), int(tp_int8), int(fuse), int(prefill_chunk), int(qkv_bias))
         self.vocab_size = vocab_size
         self.vocab_shard = vocab_size // tp_size      # lm_head is vocab-parallel: logits come back per rank shard
         self.max_batch = max_batch
