@@ -241,6 +241,24 @@ int zl_decode_attention(const void* q, const int32_t* buf_lens, void* const* k_a
                         int num_heads, int num_kv_heads, int dim_head, int bshd, void* workspace,
                         size_t workspace_bytes, int dtype, int pdl, zl_stream_t stream);
 
+/* int8 KV cache (KV_CACHE_DTYPE=int8 of the reference): KERNEL_mqa_rag_buffer_split_kv_quant
+ * (src/nn/attention/attention_kernel.cu:804-880, src/nn/attention/quant_attention.cuh:10-123).  K / V buffers per task are
+ * (len_buf, H_kv, d) uint8 = round(x * 127 / absmax) + 128, scale buffers (len_buf, H_kv) fp32 = absmax / 127 (BSHD only,
+ * like the reference); q is fp16; out in out_dtype.  Any max_len_buf (the reference only takes this path above
+ * ATTN_SPLIT_KV_THRES = 1024).  workspace as zl_decode_attention_workspace_bytes. */
+int zl_decode_attention_kv8(const void* q, const int32_t* buf_lens, void* const* k_addrs, void* const* v_addrs,
+                            void* const* scale_k_addrs, void* const* scale_v_addrs, const int8_t* mask, float scale,
+                            int max_len_buf, void* out, int B, int len_q, int num_heads, int num_kv_heads, int dim_head,
+                            void* workspace, size_t workspace_bytes, int out_dtype, int pdl, zl_stream_t stream);
+/* cache side of the same contract: int8_op::quant_calc_scale(x, 127, 128) per (token, kv head) row
+ * (src/nn/quant/int8/quant_kernel.cu:15-47) + copy_to_rag_buffer2 of the codes and of the scales
+ * (src/nn/attention/attention.cpp:656-676): k_src / v_src (T, H_kv, d), token t goes to row placement[t] of task
+ * token_batch[t] (placement < 0: skipped). */
+int zl_kv_int8_quant_append(const void* k_src, const void* v_src, const int32_t* token_batch, const int32_t* placement,
+                            void* const* k_addrs, void* const* v_addrs, void* const* scale_k_addrs,
+                            void* const* scale_v_addrs, int T, int num_kv_heads, int dim_head, int dtype, int pdl,
+                            zl_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------ *
  * Decode-step helpers around the layers
  * ------------------------------------------------------------------------------------------ */

@@ -76,6 +76,26 @@ class Ref:
                                           self.p(out)))
         return out
 
+    # ---- int8 KV cache ----
+    def quant_u8(self, x):
+        """int8_op::quant_calc_scale(x, 127, 128): (M, K) -> uint8 codes, fp32 scales"""
+        m, k = x.shape
+        q = torch.empty((m, k), dtype=torch.uint8, device=self.dev)
+        s = torch.empty(m, dtype=torch.float32, device=self.dev)
+        self._chk(self.lib.zlref_quant_calc_scale_u8(self.p(x), m, k, 0 if x.dtype == torch.float16 else 1, self.p(q), self.p(s)))
+        return q, s
+
+    def attention_kv8(self, q, lens, ks, vs, sks, svs, mask, scale, hkv, out_dtype=torch.float16):
+        b, len_q, hq, d = q.shape
+        tab = lambda ts: torch.tensor([t.data_ptr() for t in ts], dtype=torch.int64, device=self.dev)
+        ka, va, ska, sva = tab(ks), tab(vs), tab(sks), tab(svs)
+        out = torch.empty(q.shape, dtype=out_dtype, device=self.dev)
+        self._chk(self.lib.zlref_mqa_rag_buffer_quant(self.p(q), self.p(lens), self.p(ka), self.p(va), self.p(ska), self.p(sva),
+                                                      self.p(mask), ctypes.c_size_t(mask.numel()), ctypes.c_float(scale),
+                                                      int(lens.max().item()), b, len_q, hq, hkv, d,
+                                                      0 if out_dtype == torch.float16 else 1, self.p(out)))
+        return out
+
     # ---- layout ----
     def gptq_to_k_major(self, qweight, qzeros, scales, awq=False):
         lib, p = self.lib, self.p

@@ -527,4 +527,23 @@ int zlref_time_decode_layer(int D, int hq, int hkv, int d, int ff, int ctx_len, 
     }
 }
 
+// ---- int8 KV cache (KV_CACHE_DTYPE=int8): cache-side quantisation and the split-KV quant attention kernel ----
+int zlref_quant_calc_scale_u8(const void* x, int M, int K, int dtype, void* out_q, void* out_scale) {
+    ZLREF_TRY(Tensor X = wrap({(size_t)M, (size_t)K}, dt_of(dtype), x); Tensor Qo = wrap({(size_t)M, (size_t)K}, DataType::kInt8, out_q);
+              Tensor So = wrap({(size_t)M}, DataType::kFloat, out_scale); int8_op::quant_calc_scale(*g_ctx, X, &Qo, &So, 127, 128))
+}
+int zlref_mqa_rag_buffer_quant(const void* q, const void* buf_lens, const void* k_addrs, const void* v_addrs,
+                               const void* sk_addrs, const void* sv_addrs, const void* mask, size_t mask_len, float scale,
+                               int max_len_buf, int B, int len_q, int hq, int hkv, int d, int out_dtype, void* out) {
+    ZLREF_TRY(Tensor Q = wrap({(size_t)B, (size_t)len_q, (size_t)hq, (size_t)d}, DataType::kHalf, q);
+              Tensor L = wrap({(size_t)B}, DataType::kInt32, buf_lens);
+              Tensor KA = wrap({(size_t)B}, DataType::kDouble, k_addrs); Tensor VA = wrap({(size_t)B}, DataType::kDouble, v_addrs);
+              Tensor SKA = wrap({(size_t)B}, DataType::kDouble, sk_addrs); Tensor SVA = wrap({(size_t)B}, DataType::kDouble, sv_addrs);
+              Tensor M = wrap({mask_len}, DataType::kInt8, mask);
+              Tensor O = wrap({(size_t)B, (size_t)len_q, (size_t)hq, (size_t)d}, dt_of(out_dtype), out);
+              auto ws = nn::get_mqa_workspace(*g_ctx, Q, max_len_buf, true);
+              nn::multi_query_attention_rag_buffer(*g_ctx, Q, L, KA, VA, M, scale, max_len_buf, O, hq / hkv, -1, ws, SKA, SVA,
+                                                   dt_of(out_dtype)))
+}
+
 }  // extern "C"

@@ -257,3 +257,97 @@ def test_awq_native_gemm_vs_ours(lib, ref, cuda, m):
     y = ops.w4a16_gemm_fused(x, packed, n, k, variant=1).float().cpu().numpy()
     # awq_gemm sums 32 fp16 partial tensors (KERNEL_sum_dim0): it is the noisier side
     assert rel_l2(y, y_ref) <= 3e-3
+
+
+# ---- int8 KV cache: quantising append and the split-KV quant attention kernel ----
+def _kv8_case(ref, cuda, lens, hq, hkv, d, seed):
+    g = torch.Generator().manual_seed(seed)
+    b = len(lens)
+    q = torch.randn(b, 1, hq, d, generator=g).half().to(cuda)
+    ks = [torch.randn(lb, hkv, d, generator=g).half().to(cuda) for lb in lens]
+    vs = [torch.randn(lb, hkv, d, generator=g).half().to(cuda) for lb in lens]
+    masks = []
+    for lb in lens:
+        m = torch.ones(lb, dtype=torch.int8)
+        m[lb - 3:] = 0
+        m[torch.randperm(lb - 3, generator=g)[: lb // 11]] = 0
+        masks.append(m)
+    return q, ks, vs, torch.cat(masks).to(cuda), torch.tensor(lens, dtype=torch.int32, device=cuda)
+
+
+def test_kv_int8_quant_append_bit_exact_vs_reference(lib, ref, cuda):
+    """codes and scales of our cache-side quantisation == int8_op::quant_calc_scale(x, 127, 128) (quant_kernel.cu:15-47)"""
+    from zhilight_b200 import ops
+    hkv, d, t = 2, 128, 7
+    g = torch.Generator().manual_seed(3)
+    k = (torch.randn(t, hkv, d, generator=g) * 2).half().to(cuda)
+    v = torch.randn(t, hkv, d, generator=g).half().to(cuda)
+    kq_ref, ks_ref = ref.quant_u8(k.view(t * hkv, d))
+    vq_ref, vs_ref = ref.quant_u8(v.view(t * hkv, d))
+    tb = torch.tensor([0, 1, 0, 1, 0, 1, 0], dtype=torch.int32, device=cuda)
+    pl = torch.tensor([0, 0, 1, 1, 2, 2, 3], dtype=torch.int32, device=cuda)
+    kb = [torch.zeros(4, hkv, d, dtype=torch.uint8, device=cuda) for _ in range(2)]
+    vb = [torch.zeros(4, hkv, d, dtype=torch.uint8, device=cuda) for _ in range(2)]
+    sk = [torch.zeros(4, hkv, dtype=torch.float32, device=cuda) for _ in range(2)]
+    sv = [torch.zeros(4, hkv, dtype=torch.float32, device=cuda) for _ in range(2)]
+    ops.kv_int8_quant_append(k, v, tb, pl, kb, vb, sk, sv)
+    for i in range(t):
+        b_, p_ = int(tb[i]), int(pl[i])
+        assert torch.equal(kb[b_][p_], kq_ref.view(t, hkv, d)[i]) and torch.equal(vb[b_][p_], vq_ref.view(t, hkv, d)[i])
+        assert torch.equal(sk[b_][p_], ks_ref.view(t, hkv)[i]) and torch.equal(sv[b_][p_], vs_ref.view(t, hkv)[i])
+
+
+@pytest.mark.parametrize("lens", [[1600, 600], [2000], [1100, 1300, 40]])
+def test_decode_attention_kv8_vs_reference_quant_kernel(lib, ref, cuda, lens):
+    """zl_decode_attention_kv8 against KERNEL_mqa_rag_buffer_split_kv_quant (attention_kernel.cu:804-880) on the same uint8
+    caches and scales (the reference only takes its quant kernel above 1024 keys, with < 1024 keys per split).  The
+    reference multiplies q.k in fp16 (quant_attention.cuh:60-70); both must sit within 2e-3 of each other and ours
+    within 1e-3 of the fp32 evaluation of the same quantised cache."""
+    from zhilight_b200 import ops
+    hq, hkv, d = 8, 2, 128
+    q, ks, vs, mask, lens_t = _kv8_case(ref, cuda, lens, hq, hkv, d, 17)
+    kq, vq, sk, sv = [], [], [], []
+    for k, v in zip(ks, vs):
+        a, s = ref.quant_u8(k.view(-1, d))
+        kq.append(a.view(k.shape))
+        sk.append(s.view(k.shape[0], hkv))
+        a, s = ref.quant_u8(v.view(-1, d))
+        vq.append(a.view(v.shape))
+        sv.append(s.view(v.shape[0], hkv))
+    scale = 1.0 / np.sqrt(d)
+    y_ref = ref.attention_kv8(q, lens_t, kq, vq, sk, sv, mask, scale, hkv).float().cpu().numpy()
+    y = ops.decode_attention_kv8(q, lens_t, kq, vq, sk, sv, mask, scale, max(lens), hkv).float().cpu().numpy()
+    # fp32 evaluation of the same quantised cache
+    from oracle import ops as oops
+    kd = [((a.float() - 128) * s[:, :, None]).cpu().numpy() for a, s in zip(kq, sk)]
+    vd = [((a.float() - 128) * s[:, :, None]).cpu().numpy() for a, s in zip(vq, sv)]
+    off = np.cumsum([0] + lens)
+    masks = [mask[off[i]:off[i + 1]].cpu().numpy().reshape(1, -1) for i in range(len(lens))]
+    exact = oops.decode_attention(q.cpu().numpy(), kd, vd, lens, masks, scale, hq // hkv, "f32")
+    assert rel_l2(y, exact) <= 1e-3
+    assert rel_l2(y, y_ref) <= 2e-3
+    assert rel_l2(y, exact) <= rel_l2(y_ref, exact) + 2e-4       # at least as close to the exact result as the reference
+
+
+def test_decode_attention_kv8_short_context_and_gqa4(lib, cuda):
+    """below the reference's split threshold (its quant kernel is never taken there) and with m_query = 4: against the fp32
+    evaluation of the quantised cache"""
+    from zhilight_b200 import ops
+    from oracle import ops as oops
+    hq, hkv, d = 8, 2, 128
+    lens = [130, 17, 512]
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(3, 1, hq, d, generator=g).half().to(cuda)
+    kq = [torch.randint(0, 256, (lb, hkv, d), generator=g, dtype=torch.uint8).to(cuda) for lb in lens]
+    vq = [torch.randint(0, 256, (lb, hkv, d), generator=g, dtype=torch.uint8).to(cuda) for lb in lens]
+    sk = [(0.01 + 0.01 * torch.rand(lb, hkv, generator=g)).to(cuda) for lb in lens]
+    sv = [(0.01 + 0.01 * torch.rand(lb, hkv, generator=g)).to(cuda) for lb in lens]
+    lens_t = torch.tensor(lens, dtype=torch.int32, device=cuda)
+    mask = torch.ones(sum(lens), dtype=torch.int8, device=cuda)
+    scale = 1.0 / np.sqrt(d)
+    y = ops.decode_attention_kv8(q, lens_t, kq, vq, sk, sv, mask, scale, max(lens), hkv).float().cpu().numpy()
+    kd = [((a.float() - 128) * s[:, :, None]).cpu().numpy() for a, s in zip(kq, sk)]
+    vd = [((a.float() - 128) * s[:, :, None]).cpu().numpy() for a, s in zip(vq, sv)]
+    masks = [np.ones((1, lb), np.int8) for lb in lens]
+    exact = oops.decode_attention(q.cpu().numpy(), kd, vd, lens, masks, scale, hq // hkv, "f32")
+    assert rel_l2(y, exact) <= 1e-3

@@ -12,6 +12,9 @@
 // Splits are merged with the reference's LSE rule (attention_kernel.cu:881-923).
 #include "common.cuh"
 #include "decode_attn_short.cuh"
+#include "decode_attn_warp.cuh"
+
+#include <cstdlib>
 
 namespace zl {
 
@@ -322,8 +325,17 @@ extern "C" int zl_decode_attention(const void* q, const int32_t* buf_lens, void*
     }
     const int hgroups = (m_query + 7) / 8;
     dim3 grid(splits, num_kv_heads * hgroups, B * len_q), block(kAttnThreads);
+    // default for the latency regime: the warp-per-32-keys kernel (one __syncthreads per CTA); ZL_ATTN_OLD_SHORT=1 keeps the
+    // previous 512-thread short kernel for A/B measurements
+    static const bool old_short = getenv("ZL_ATTN_OLD_SHORT") != nullptr;
+    const bool use_warp = use_short && !old_short;
 #define ZL_ATTN_LAUNCH(TT, DD)                                                                                  \
-    if (use_short) {                                                                                            \
+    if (use_warp) {                                                                                             \
+        ZL_CHECK_CUDA(launch(k_decode_attn_warp<TT, DD>, grid, dim3(kWarpAttnWarps * 32),                       \
+                             (size_t)warp_attn_smem_floats<DD>() * sizeof(float), stream, pdl != 0, (const TT*)q, \
+                             buf_lens, (TT* const*)k_addrs, (TT* const*)v_addrs, mask, scale, (TT*)out, part_o, \
+                             part_m, part_l, len_q, num_heads, num_kv_heads, m_query, splits, bshd));            \
+    } else if (use_short) {                                                                                     \
         static bool attr_set = false;                                                                           \
         if (!attr_set) {                                                                                        \
             ZL_CHECK_CUDA(cudaFuncSetAttribute(k_decode_attn_short<TT, DD>,                                     \

@@ -353,6 +353,31 @@ def decode_attention(q, buf_lens, k_bufs, v_bufs, mask, scale, max_len_buf, num_
     return out
 
 
+def decode_attention_kv8(q, buf_lens, k_bufs, v_bufs, sk_bufs, sv_bufs, mask, scale, max_len_buf, num_kv_heads, out_dtype=None,
+                         pdl=False):
+    """int8 KV cache attention: q (B, len_q, H_q, d) f16; k/v lists of (len_buf, H_kv, d) uint8; sk/sv lists of
+    (len_buf, H_kv) fp32 scales."""
+    b, len_q, hq, d = q.shape
+    out = torch.empty(q.shape, dtype=out_dtype or q.dtype, device=q.device)
+    ws_bytes = _lib.load().zl_decode_attention_workspace_bytes(b, len_q, hq, d, max_len_buf)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
+    tabs = [_ptr_table(x, q.device) for x in (k_bufs, v_bufs, sk_bufs, sv_bufs)]
+    _lib.call("zl_decode_attention_kv8", _p(q), _p(buf_lens), _p(tabs[0]), _p(tabs[1]), _p(tabs[2]), _p(tabs[3]), _p(mask),
+              float(scale), max_len_buf, _p(out), b, len_q, hq, num_kv_heads, d, _p(ws), ws_bytes, _dt(out), int(pdl),
+              _stream())
+    torch.cuda.current_stream().synchronize()
+    return out
+
+
+def kv_int8_quant_append(k_src, v_src, token_batch, placement, k_bufs, v_bufs, sk_bufs, sv_bufs):
+    """k_src / v_src (T, H_kv, d) -> uint8 codes + fp32 scales scattered into the per-task caches."""
+    t, hkv, d = k_src.shape
+    tabs = [_ptr_table(x, k_src.device) for x in (k_bufs, v_bufs, sk_bufs, sv_bufs)]
+    _lib.call("zl_kv_int8_quant_append", _p(k_src), _p(v_src), _p(token_batch), _p(placement), _p(tabs[0]), _p(tabs[1]),
+              _p(tabs[2]), _p(tabs[3]), t, hkv, d, _dt(k_src), 0, _stream())
+    torch.cuda.current_stream().synchronize()
+
+
 def embedding(ids, table):
     t = ids.numel()
     out = torch.empty((t, table.shape[1]), dtype=table.dtype, device=table.device)
