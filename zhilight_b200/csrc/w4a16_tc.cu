@@ -21,14 +21,12 @@
 #include "common.cuh"
 #include "w4_layout.cuh"
 #include "w4_params.h"
-
-#include <cuda.h>
+#include "tc_common.cuh"
 
 #include <cstdlib>
 
 namespace zl {
 
-constexpr int kTcRows = 128;                        // weight rows per tile = UMMA M = TMEM lanes
 constexpr int kTcRawStage = 4 * kW4BlockBytes;      // 4 blocks of 32 rows
 constexpr int kTcAStage = 2 * kTcRows * 128;        // [k atom (64 k)][row][128 B]
 constexpr int kTcWarpRaw = 0, kTcWarpX = 1, kTcWarpMma = 2, kTcWarpDq0 = 3, kTcDqWarps = 8, kTcWarpEpi0 = 11;
@@ -70,45 +68,6 @@ struct alignas(64) W4TcParams {
     int num_heads, num_kv_heads, dim_head;
 };
 
-// ---- PTX wrappers -------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// bounded wait: a protocol bug must not hang the GPU (2 s, then the watchdog code is published and the kernel traps)
-__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, unsigned* err, unsigned code) {
-    if (mbar_try_wait(bar, parity)) return;
-    const unsigned long long t0 = globaltimer_ns();
-    while (!mbar_try_wait(bar, parity)) {
-        if (globaltimer_ns() - t0 > 2000000000ull) {
-            if (err) atomicExch(err, code);
-            __threadfence_system();
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
-            "r"(smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start address
-// >> 4, LBO (unused for swizzled K-major, canonical value 1), SBO = 1024 B between 8-row groups, version 1, layout 2.
-__device__ __forceinline__ uint64_t tc_desc_sw128(uint32_t saddr) {
-    uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
 // instruction descriptor, kind::f16: D f32 (bits 4-5 = 1), A/B f16 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 __host__ __device__ constexpr uint32_t tc_idesc_f16(int n) {
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
@@ -120,18 +79,6 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // One 32-bit ZLW4I word = 4 consecutive k of row g (low nibbles) and of row g + 8 (high nibbles) -> 2 x 2 half2.
 // 0x64xx is 1024 + x for x < 1024; 0x54xx is 64 + x / 16: the high nibble never has to be shifted.
@@ -473,33 +420,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_w4a16_tc(const __grid_constan
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn tc_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* sym = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(sym);
-    }
-    return fn;
-}
-
-struct TcDeviceState {
-    float* ws = nullptr;
-    unsigned* counters = nullptr;
-    unsigned* err = nullptr;
-    size_t ws_bytes = 0;
-};
 static TcDeviceState g_tc_state[64];
-constexpr size_t kTcWsBytes = 64ull << 20;   // >= 2 x 148 items x 256 tokens x 128 rows x 4 B
-constexpr int kTcMaxTiles = 8192;
 
-static TcDeviceState* tc_state() {
+TcDeviceState* tc_state() {
     int dev = 0;
     cudaGetDevice(&dev);
     return (dev >= 0 && dev < 64) ? &g_tc_state[dev] : nullptr;
@@ -575,17 +498,11 @@ extern "C" int zl_w4_tc_set_splits(int splits) {
 
 cudaError_t launch_w4_tc(const W4Params& p, bool pdl, cudaStream_t stream) {
     TcDeviceState* st = tc_state();
-    EncodeTiledFn enc = tc_encode_fn();
-    if (!st || !st->ws || !enc) return cudaErrorNotSupported;
+    if (!st || !st->ws) return cudaErrorNotSupported;
     const int ntok = p.mc <= 32 ? 32 : p.mc <= 64 ? 64 : p.mc <= 128 ? 128 : 256;
     W4TcParams q;
-    const cuuint64_t gdim[2] = {(cuuint64_t)p.K, (cuuint64_t)p.mc};
-    const cuuint64_t gstride[1] = {(cuuint64_t)p.ldx * 2};
-    const cuuint32_t box[2] = {64u, (cuuint32_t)ntok};
-    const cuuint32_t estr[2] = {1u, 1u};
-    if (enc(&q.xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(p.x), gdim, gstride, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    if (!tc_make_map_2d(&q.xmap, p.x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)p.mc, (uint64_t)p.K, (uint64_t)p.ldx * 2,
+                        (uint32_t)ntok))
         return cudaErrorInvalidValue;
     q.packed = p.packed;
     q.bias = p.bias;

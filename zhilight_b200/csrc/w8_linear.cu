@@ -15,6 +15,14 @@
 // Small N is covered by splitting K across the warps of a CTA (int32 partial sums add exactly).
 #include "common.cuh"
 
+namespace zl {
+// tcgen05 W8A8 kernel (w8_tc.cu)
+bool w8_tc_supports(int N, int K);
+template <typename T, bool FP8>
+cudaError_t launch_w8_tc(const uint8_t* xq, const float* sx, const uint8_t* w, const void* sw, int sw_mode, const T* bias, T* y,
+                         int mc, int N, int K, bool pdl, cudaStream_t stream);
+}  // namespace zl
+
 #include <cuda_fp8.h>
 
 namespace zl {
@@ -432,6 +440,40 @@ extern "C" int zl_w8a8_gemm(const void* xq, const float* x_scale, const void* w,
     const uint8_t* xq8 = static_cast<const uint8_t*>(xq);
     const uint8_t* w8 = static_cast<const uint8_t*>(w);
     const int sw_f32 = kind == ZL_W8_FP8_ROWS ? 2 : (w_scale_dtype == ZL_F32 ? 1 : 0);
+    if (w8_tc_supports(N, K)) {
+        // tcgen05 path (w8_tc.cu): both operands through the TMA engine, s32 / f32 accumulators in TMEM
+        {
+            static bool prepared[64] = {};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (dev < 0 || dev >= 64 || !prepared[dev]) {
+                int rc = zl_prepare();
+                if (rc != ZL_OK) return rc;
+                if (dev >= 0 && dev < 64) prepared[dev] = true;
+            }
+        }
+        const bool fp8 = kind != ZL_W8_INT8;
+        const int sw_mode = fp8 ? (kind == ZL_W8_FP8_ROWS ? 2 : 3) : sw_f32;
+        for (int m0 = 0; m0 < M; m0 += 256) {
+            const int mc = (M - m0) < 256 ? (M - m0) : 256;
+            const bool p = pdl != 0 && m0 == 0;
+            const float* sx = kind == ZL_W8_INT8 ? x_scale + m0 : x_scale;
+            cudaError_t e;
+            if (dtype == ZL_F16) {
+                const __half* b = static_cast<const __half*>(bias);
+                __half* yo = static_cast<__half*>(y) + (size_t)m0 * N;
+                e = fp8 ? launch_w8_tc<__half, true>(xq8 + (size_t)m0 * K, sx, w8, w_scale, sw_mode, b, yo, mc, N, K, p, stream)
+                        : launch_w8_tc<__half, false>(xq8 + (size_t)m0 * K, sx, w8, w_scale, sw_mode, b, yo, mc, N, K, p, stream);
+            } else {
+                const __nv_bfloat16* b = static_cast<const __nv_bfloat16*>(bias);
+                __nv_bfloat16* yo = static_cast<__nv_bfloat16*>(y) + (size_t)m0 * N;
+                e = fp8 ? launch_w8_tc<__nv_bfloat16, true>(xq8 + (size_t)m0 * K, sx, w8, w_scale, sw_mode, b, yo, mc, N, K, p, stream)
+                        : launch_w8_tc<__nv_bfloat16, false>(xq8 + (size_t)m0 * K, sx, w8, w_scale, sw_mode, b, yo, mc, N, K, p, stream);
+            }
+            ZL_CHECK_CUDA(e);
+        }
+        return ZL_OK;
+    }
     for (int m0 = 0; m0 < M; m0 += 32) {
         const int mc = (M - m0) < 32 ? (M - m0) : 32;
         const bool p = pdl != 0 && m0 == 0;
