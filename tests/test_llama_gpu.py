@@ -259,3 +259,39 @@ def test_qkv_bias_model_matches_oracle(lib, cuda, cfg):
     sd2 = {k: v for k, v in sd.items() if not k.endswith(".bias")}
     ref_nobias = omodel.OracleLlama(cfg, sd2, 5, 128, False, "f16", fuse_norm=True).decode(np.array([3]), [0])
     assert rel_l2(orc.decode(np.array([3]), [0]), ref_nobias) > 1e-2
+
+
+LAYERS8B_SMALLV = dict(num_layers=2, dim_model=4096, num_heads=32, num_kv_heads=8, dim_head=128, dim_ff=14336, vocab_size=2048,
+                       eps=1e-5, rope_theta=500000.0, rope_llama3=dict(factor=8.0, low=1.0, high=4.0, orig=8192.0))
+
+
+@pytest.mark.parametrize("b,graph,pdl", [(20, True, True), (32, True, True), (32, False, True), (32, False, False), (17, True, False)])
+def test_large_batch_decode_on_8b_shapes_matches_batch_1(lib, cuda, b, graph, pdl):
+    """Batch 17..32 decode runs the tcgen05 GEMMs (split-k, qkv-RoPE / SwiGLU / residual epilogues) inside the CUDA graph
+    with programmatic dependent launch on Llama-3.1-8B layer shapes: every task of a batch of identical tokens must
+    reproduce the batch-1 logits (exact-integer kernel) to fp16 accuracy, with and without graph / PDL."""
+    from zhilight_b200.llama import LlamaDecoder
+    cfg = LAYERS8B_SMALLV
+
+    def run(bb, feed):
+        dec = LlamaDecoder(quant_type=5, group_size=128, sym=True, max_batch=bb, max_seq=64, use_graph=graph, use_pdl=pdl, **cfg)
+        dec.init_synthetic(seed=3)
+        res, fed = [], []
+        tok = 7
+        for step in range(4):
+            if feed is not None:
+                tok = feed[step]
+            fed.append(tok)
+            nxt, logits = dec.decode(np.full(bb, tok, dtype=np.int32), np.full(bb, step, dtype=np.int32), want_logits=True)
+            res.append(logits.copy())
+            tok = int(nxt[0])
+        dec.close()
+        return res, fed
+
+    ref, fed = run(1, None)
+    out, _ = run(b, fed)
+    for step, (l1, lb) in enumerate(zip(ref, out)):
+        assert np.isfinite(l1).all(), step
+        assert np.isfinite(lb).all(), step
+        for t in (0, b // 2, b - 1):
+            assert rel_l2(lb[t], l1[0]) <= 5e-3, (step, t)

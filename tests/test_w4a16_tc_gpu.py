@@ -40,7 +40,9 @@ def _check_watchdog(lib):
 
 def test_route_selects_tcgen05(lib):
     assert lib.zl_w4_int_layout_route(1, 4096, 4096) == 3       # exact-integer mma.sync kernel
-    assert lib.zl_w4_int_layout_route(16, 4096, 4096) == 3
+    assert lib.zl_w4_int_layout_route(8, 4096, 4096) == 3
+    assert lib.zl_w4_int_layout_route(16, 1024, 4096) == 3
+    assert lib.zl_w4_int_layout_route(16, 4096, 4096) == 4      # 16 staged token rows of K = 4096 do not fit beside the rings
     assert lib.zl_w4_int_layout_route(17, 4096, 4096) == 4      # tcgen05
     assert lib.zl_w4_int_layout_route(32, 4096, 14336) == 4
     assert lib.zl_w4_int_layout_route(8, 4096, 14336) == 4      # staged activations of the integer kernel do not fit
@@ -119,8 +121,9 @@ def test_bias_residual_swiglu(lib, cuda, splits, m, s):
     assert rel_l2(y2, ref2) <= TOL
 
 
-@pytest.mark.parametrize("d,hq,hkv,k,t", [(128, 4, 2, 512, 24), (64, 4, 2, 256, 40), (128, 8, 1, 1024, 130)])
-def test_qkv_rope_epilogue(lib, cuda, d, hq, hkv, k, t):
+@pytest.mark.parametrize("d,hq,hkv,k,t,s", [(128, 4, 2, 512, 24, 0), (64, 4, 2, 256, 40, 0), (128, 8, 1, 1024, 130, 0),
+                                           (128, 32, 8, 4096, 32, 0), (128, 32, 8, 4096, 20, 3), (128, 8, 2, 2048, 32, 2)])
+def test_qkv_rope_epilogue(lib, cuda, splits, d, hq, hkv, k, t, s):
     """fused qkv split + RoPE + KV append vs the stand-alone rope/append operator on the plain GEMM output"""
     from zhilight_b200 import ops
     n = (hq + 2 * hkv) * d
@@ -136,11 +139,14 @@ def test_qkv_rope_epilogue(lib, cuda, d, hq, hkv, k, t):
     slots = t // 3 + 2
     kb = [torch.zeros(slots, hkv, d, dtype=torch.float16, device=cuda) for _ in range(3)]
     vb = [torch.zeros(slots, hkv, d, dtype=torch.float16, device=cuda) for _ in range(3)]
+    splits(s)
     q = ops.w4a16_gemm_fused(x, packed, n, k, epilogue=ops.EPI_QKV_ROPE, variant=1,
                              rope=dict(cos=cos, sin=sin, token_batch=tb, placement=pl, k_bufs=kb, v_bufs=vb,
                                        num_heads=hq, num_kv_heads=hkv, dim_head=d))
     _check_watchdog(lib)
+    splits(0)
     qkv = ops.w4a16_gemm_fused(x, packed_plain, n, k, variant=1)
+    assert torch.isfinite(q).all() and torch.isfinite(qkv).all()
     kb2 = [torch.zeros_like(b) for b in kb]
     vb2 = [torch.zeros_like(b) for b in vb]
     q2 = ops.qkv_rope_append(cos, sin, qkv, tb, pl, kb2, vb2, hq, hkv, d)
