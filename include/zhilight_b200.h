@@ -254,6 +254,8 @@ int zl_decode_attention_kv8(const void* q, const int32_t* buf_lens, void* const*
  * (src/nn/quant/int8/quant_kernel.cu:15-47) + copy_to_rag_buffer2 of the codes and of the scales
  * (src/nn/attention/attention.cpp:656-676): k_src / v_src (T, H_kv, d), token t goes to row placement[t] of task
  * token_batch[t] (placement < 0: skipped). */
+/* the same quantisation on dense rows: x (M, K) -> q (M, K) uint8, scale (M) fp32 (quant_calc_scale(x, 127, 128)). */
+int zl_int8_quant_rows_u8(const void* x, void* q, float* scale, int M, int K, int dtype, zl_stream_t stream);
 int zl_kv_int8_quant_append(const void* k_src, const void* v_src, const int32_t* token_batch, const int32_t* placement,
                             void* const* k_addrs, void* const* v_addrs, void* const* scale_k_addrs,
                             void* const* scale_v_addrs, int T, int num_kv_heads, int dim_head, int dtype, int pdl,

@@ -18,6 +18,7 @@
 #include "nn/layernorm/layernorm.h"
 #include "nn/linear/activation_kernel.h"
 #include "nn/position/rotary_embedding.h"
+#include "nn/position/rope_preparer.h"
 #include "nn/quant/fp8/fp8.h"
 #include "nn/quant/gptq/gptq.h"
 #include "nn/quant/int8/quant_kernel.h"
@@ -296,16 +297,57 @@ void multi_query_attention_rag_buffer(const core::Context& ctx, const Tensor& ba
                                       const Tensor& scale_val_addrs, DataType dequant_dtype) {
     (void)algo_id;
     (void)ws;
-    (void)dequant_dtype;
-    BM_ASSERT_EQ(scale_key_addrs.numel(), 0, "int8 KV is not on this path");
-    BM_ASSERT_EQ(scale_val_addrs.numel(), 0, "int8 KV is not on this path");
     const int B = (int)batch_q.size(0), len_q = (int)batch_q.size(1), Hq = (int)batch_q.size(2), d = (int)batch_q.size(3);
     const size_t wsb = zl_decode_attention_workspace_bytes(B, len_q, Hq, d, max_len_buf);
     Tensor work = ctx.tensor({wsb}, DataType::kInt8);
+    if (scale_key_addrs.numel()) {
+        // int8 KV cache (KERNEL_mqa_rag_buffer_split_kv_quant, attention_kernel.cu:804-880): uint8 codes + fp32 scales
+        BM_ASSERT_EQ(batch_q.dtype(), DataType::kHalf, "input must be half");
+        BM_ASSERT(ctx.is_BSHD(), "int8 KV cache is BSHD");
+        ZL_THROW_IF(zl_decode_attention_kv8(batch_q.data(), buf_lens.data<int32_t>(), key_buf_addrs.data<void*>(),
+                                            val_buf_addrs.data<void*>(), scale_key_addrs.data<void*>(),
+                                            scale_val_addrs.data<void*>(), mask.numel() ? mask.data<int8_t>() : nullptr, scale,
+                                            max_len_buf, output.data(), B, len_q, Hq, Hq / m_query, d, work.data(), wsb,
+                                            zl_dt(dequant_dtype), 0, st(ctx)));
+        return;
+    }
     ZL_THROW_IF(zl_decode_attention(batch_q.data(), buf_lens.data<int32_t>(), key_buf_addrs.data<void*>(),
                                     val_buf_addrs.data<void*>(), mask.numel() ? mask.data<int8_t>() : nullptr, scale,
                                     max_len_buf, output.data(), B, len_q, Hq, Hq / m_query, d, ctx.is_BSHD() ? 1 : 0,
                                     work.data(), wsb, zl_dt(batch_q.dtype()), 0, st(ctx)));
+}
+
+// the reference sizes its split workspace here (attention_kernel.cu:1237-1250); ours is allocated inside the wrapper above
+AttentionWorkspace get_mqa_workspace(const core::Context& ctx, const Tensor& batch_q, int max_len_buf, bool is_quantized) {
+    (void)max_len_buf;
+    (void)is_quantized;
+    const size_t vheads = batch_q.numel() / batch_q.size(-1);
+    return {ctx.tensor({vheads, 1, batch_q.size(-1)}, DataType::kFloat), ctx.tensor({vheads, 1}, DataType::kFloat),
+            ctx.tensor({vheads, 1}, DataType::kFloat)};
+}
+
+// RopePreparer (rope_preparer.cu:49-233): cos / sin tables, plain and llama3 wavelength scaling
+class RopePreparer::impl {
+public:
+    model::ModelConfig cfg;
+    explicit impl(model::ModelConfig c) : cfg(std::move(c)) {}
+};
+RopePreparer::RopePreparer(const core::Context& ctx, model::ModelConfig cfg) : pimpl(new impl(std::move(cfg))) { (void)ctx; }
+RopePreparer::~RopePreparer() {}
+std::tuple<Tensor, Tensor> RopePreparer::forward(const core::Context& ctx, const Tensor& tokens, const Tensor& pos) {
+    (void)tokens;
+    const model::ModelConfig& c = pimpl->cfg;
+    const int d = c.qk_rope_head_dim > 0 ? c.qk_rope_head_dim : c.dim_head;
+    auto shape = pos.shape();
+    shape.push_back((size_t)d);
+    Tensor cos = ctx.tensor(shape, DataType::kFloat), sin = ctx.tensor(shape, DataType::kFloat);
+    const bool l3 = c.rope_cfg.type == "llama3";
+    if (!l3 && c.rope_cfg.type != "") throw std::runtime_error("RopePreparer: Not implemented rope type: " + c.rope_cfg.type);
+    ZL_THROW_IF(zl_rope_cos_sin(pos.data<int32_t>(), cos.mutable_data<float>(), sin.mutable_data<float>(), (int)pos.numel(), d,
+                                c.rope_theta, l3 ? c.rope_cfg.factor : 0.f, c.rope_cfg.low_freq_factor,
+                                c.rope_cfg.high_freq_factor, (float)c.rope_cfg.original_max_position,
+                                c.rope_cfg.neox_style ? 1 : 0, st(ctx)));
+    return {cos, sin};
 }
 
 }  // namespace nn
@@ -317,10 +359,15 @@ namespace int8_op {
 
 void quant_calc_scale(const core::Context& ctx, const Tensor& input, Tensor* output, Tensor* output_scale, int q_max,
                       int q_zero) {
-    BM_ASSERT(q_max == 127 && q_zero == 0, "per-token symmetric int8 only");
+    BM_ASSERT(q_max == 127 && (q_zero == 0 || q_zero == 128), "per-token int8 (q_zero 0) or the uint8 KV-cache form (q_zero 128)");
     const int K = (int)input.size(-1), M = (int)rows_of(input);
     if (output->shape() != input.shape()) *output = ctx.tensor(input.size(), DataType::kInt8);
     if (output_scale->numel() != (size_t)M) *output_scale = ctx.tensor({(size_t)M}, DataType::kFloat);
+    if (q_zero == 128) {
+        ZL_THROW_IF(zl_int8_quant_rows_u8(input.data(), output->data(), output_scale->mutable_data<float>(), M, K,
+                                          zl_dt(input.dtype()), st(ctx)));
+        return;
+    }
     ZL_THROW_IF(zl_int8_quant_per_token(input.data(), K, output->data(), output_scale->mutable_data<float>(), M, K,
                                         zl_dt(input.dtype()), 0, st(ctx)));
 }

@@ -146,6 +146,22 @@ def check_marlin(g):
     np.testing.assert_array_equal(nib(g["repacked"]), nib(np.ascontiguousarray(c["qweight"])))
 
 
+def check_kv8(g):
+    c = gc.case_kv8()
+    kd, vd = [], []
+    for i, (k, v) in enumerate(zip(c["ks"], c["vs"])):
+        kq, sk = ops.int8_quant_per_token(k.reshape(-1, c["d"]))        # same absmax / 127 rounding, codes offset by 128
+        vq, sv = ops.int8_quant_per_token(v.reshape(-1, c["d"]))
+        np.testing.assert_array_equal(g["kq%d" % i].reshape(-1, c["d"]).astype(np.int32) - 128, kq.astype(np.int32))
+        np.testing.assert_array_equal(g["vq%d" % i].reshape(-1, c["d"]).astype(np.int32) - 128, vq.astype(np.int32))
+        np.testing.assert_array_equal(g["sk%d" % i].reshape(-1), sk)
+        np.testing.assert_array_equal(g["sv%d" % i].reshape(-1), sv)
+        kd.append((kq.astype(np.float32) * sk[:, None]).reshape(k.shape))
+        vd.append((vq.astype(np.float32) * sv[:, None]).reshape(v.shape))
+    ref = ops.decode_attention(c["q"], kd, vd, c["lens"], c["masks"], c["scale"], c["hq"] // c["hkv"], "f32")
+    assert _rel(g["out"], ref) < 3e-3, _rel(g["out"], ref)          # the reference multiplies q.k in fp16
+
+
 CHECKS = {
     "ref_gptq_layout": lambda g: check_layout(g, False),
     "ref_awq_layout": lambda g: check_layout(g, True),
@@ -160,6 +176,7 @@ CHECKS = {
     "ref_w8": check_w8,
     "ref_rope_tables": check_rope_tables,
     "ref_marlin": check_marlin,
+    "ref_kv8": check_kv8,
 }
 
 

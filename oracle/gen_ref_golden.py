@@ -363,15 +363,29 @@ def main(out_dir, lib_path=None):
         outs["f8_y_bias_" + tag] = n(ref.fp8_gemm(fq, fs, ref.t(c["w_f8"]), sw8, ref.t(c["bias"]).to(dt), dt).float())
     np.savez(os.path.join(out_dir, "ref_w8.npz"), **outs)
 
-    if not hasattr(ref.lib, "zlref_rope_cos_sin"):     # the drop-in library has no counterpart of the round-2 shim
-        print("wrote goldens to", out_dir)
-        return
     c = gc.case_rope_tables()
     outs = {}
     for name, (d, theta, l3) in c["variants"].items():
         cos, sin = ref.rope_cos_sin(ref.t(c["pos"]), d, theta, l3)
         outs["cos_" + name], outs["sin_" + name] = n(cos), n(sin)
     np.savez(os.path.join(out_dir, "ref_rope_tables.npz"), **outs)
+
+    c = gc.case_kv8()
+    outs = {}
+    kq, vq, sk, sv = [], [], [], []
+    for i, (k, v) in enumerate(zip(c["ks"], c["vs"])):
+        a, s = ref.quant_u8(ref.t(k.reshape(-1, c["d"])))
+        kq.append(a.view(k.shape)); sk.append(s.view(k.shape[0], c["hkv"]))
+        b, s2 = ref.quant_u8(ref.t(v.reshape(-1, c["d"])))
+        vq.append(b.view(v.shape)); sv.append(s2.view(v.shape[0], c["hkv"]))
+        outs["kq%d" % i], outs["sk%d" % i], outs["vq%d" % i], outs["sv%d" % i] = n(kq[-1]), n(sk[-1]), n(vq[-1]), n(sv[-1])
+    mask = ref.t(np.concatenate([m.reshape(-1) for m in c["masks"]]))
+    outs["out"] = n(ref.attention_kv8(ref.t(c["q"]), ref.t(c["lens"]), kq, vq, sk, sv, mask, c["scale"], c["hkv"]).float())
+    np.savez(os.path.join(out_dir, "ref_kv8.npz"), **outs)
+
+    if not hasattr(ref.lib, "zlref_marlin_gemm"):     # the drop-in library has no counterpart of the reference-only shim
+        print("wrote goldens to", out_dir)
+        return
 
     c = gc.case_marlin()
     outs = {"repacked": n(ref.marlin_repack(ref.t(c["qweight"])))}

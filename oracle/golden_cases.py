@@ -126,3 +126,26 @@ def case_marlin():
     r = _rng(132)
     xs = {m: r.standard_normal((m, k)).astype(np.float16) for m in (1, 5, 17)}
     return dict(qweight=qw, qzeros=qz, scales=sc, g_idx=gi, xs=xs, K=k, N=n, G=k // g)
+
+
+def case_kv8():
+    """int8 KV cache (KV_CACHE_DTYPE=int8): fp16 K / V rows that all share one absmax (4.0) per (row, head) -- see
+    tests/test_vs_reference_gpu.py for why: the reference's split kernel indexes its scales without the split offset."""
+    r = _rng(141)
+    hq, hkv, d = 8, 2, 128
+    lens = [1100, 1300, 40]
+    q = r.standard_normal((len(lens), 1, hq, d)).astype(np.float16)
+    ks, vs, masks = [], [], []
+    for lb in lens:
+        k = np.clip(r.standard_normal((lb, hkv, d)), -4, 4).astype(np.float16)
+        v = np.clip(r.standard_normal((lb, hkv, d)), -4, 4).astype(np.float16)
+        k[:, :, 5] = 4.0
+        v[:, :, 5] = 4.0
+        ks.append(k)
+        vs.append(v)
+        m = np.ones((1, lb), np.int8)
+        m[0, lb - 2:] = 0
+        m[0, r.permutation(lb - 2)[: lb // 9]] = 0
+        masks.append(m)
+    return dict(q=q, ks=ks, vs=vs, masks=masks, lens=np.array(lens, np.int32), hq=hq, hkv=hkv, d=d,
+                scale=float(1.0 / np.sqrt(d)))

@@ -20,6 +20,7 @@
 #include "nn/block/block_kernel.h"
 #include "nn/linear/activation_kernel.h"
 #include "kvcache/ragged_buffer_kernel.h"
+#include "nn/position/rope_preparer.h"
 
 #include <cstdio>
 #include <cstring>
@@ -290,6 +291,35 @@ int zlref_time_gptq_gemv(const void* a, const void* const* qw_list, const void* 
         snprintf(g_err, sizeof(g_err), "%s", e.what());
         return -1;
     }
+}
+
+// ---- RopePreparer (src/nn/position/rope_preparer.cu:49-233): cos/sin tables, plain and llama3 ----
+int zlref_rope_cos_sin(const void* pos, int T, int d, float theta, int llama3, float factor, float low, float high,
+                       int orig_ctx, void* out_cos, void* out_sin) {
+    ZLREF_TRY(model::ModelConfig cfg("llama", 1, 64, 1, d, 64, 64); cfg.rope_theta = theta;
+              if (llama3) { cfg.rope_cfg.type = "llama3"; cfg.rope_cfg.factor = factor; cfg.rope_cfg.low_freq_factor = low;
+                            cfg.rope_cfg.high_freq_factor = high; cfg.rope_cfg.original_max_position = orig_ctx; }
+              nn::RopePreparer prep(*g_ctx, cfg); Tensor P = wrap({(size_t)T}, DataType::kInt32, pos);
+              auto cs = prep.forward(*g_ctx, P, P); copy_out(std::get<0>(cs), out_cos); copy_out(std::get<1>(cs), out_sin))
+}
+
+// ---- int8 KV cache (KV_CACHE_DTYPE=int8): cache-side quantisation and the split-KV quant attention kernel ----
+int zlref_quant_calc_scale_u8(const void* x, int M, int K, int dtype, void* out_q, void* out_scale) {
+    ZLREF_TRY(Tensor X = wrap({(size_t)M, (size_t)K}, dt_of(dtype), x); Tensor Qo = wrap({(size_t)M, (size_t)K}, DataType::kInt8, out_q);
+              Tensor So = wrap({(size_t)M}, DataType::kFloat, out_scale); int8_op::quant_calc_scale(*g_ctx, X, &Qo, &So, 127, 128))
+}
+int zlref_mqa_rag_buffer_quant(const void* q, const void* buf_lens, const void* k_addrs, const void* v_addrs,
+                               const void* sk_addrs, const void* sv_addrs, const void* mask, size_t mask_len, float scale,
+                               int max_len_buf, int B, int len_q, int hq, int hkv, int d, int out_dtype, void* out) {
+    ZLREF_TRY(Tensor Q = wrap({(size_t)B, (size_t)len_q, (size_t)hq, (size_t)d}, DataType::kHalf, q);
+              Tensor L = wrap({(size_t)B}, DataType::kInt32, buf_lens);
+              Tensor KA = wrap({(size_t)B}, DataType::kDouble, k_addrs); Tensor VA = wrap({(size_t)B}, DataType::kDouble, v_addrs);
+              Tensor SKA = wrap({(size_t)B}, DataType::kDouble, sk_addrs); Tensor SVA = wrap({(size_t)B}, DataType::kDouble, sv_addrs);
+              Tensor M = wrap({mask_len}, DataType::kInt8, mask);
+              Tensor O = wrap({(size_t)B, (size_t)len_q, (size_t)hq, (size_t)d}, dt_of(out_dtype), out);
+              auto ws = nn::get_mqa_workspace(*g_ctx, Q, max_len_buf, true);
+              nn::multi_query_attention_rag_buffer(*g_ctx, Q, L, KA, VA, M, scale, max_len_buf, O, hq / hkv, -1, ws, SKA, SVA,
+                                                   dt_of(out_dtype)))
 }
 
 }  // extern "C"

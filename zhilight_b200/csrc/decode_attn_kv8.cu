@@ -276,9 +276,39 @@ __global__ void k_kv8_quant_append(const T* __restrict__ k_src, const T* __restr
     if (c == 0) (is_v ? sv_addrs : sk_addrs)[b][(size_t)pl * num_kv_heads + hk] = amax / 127.0f;
 }
 
+// dense form of the same quantisation: int8_op::quant_calc_scale(x, 127, 128) on (M, K) rows -> uint8 codes + fp32 scales
+template <typename T>
+__global__ void k_int8_quant_rows_u8(const T* __restrict__ x, uint8_t* __restrict__ q, float* __restrict__ scale, int K) {
+    __shared__ float s_max[32];
+    const size_t off = (size_t)blockIdx.x * K;
+    float amax = 0.f;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) amax = fmaxf(amax, fabsf(to_f32<T>(x[off + i])));
+    amax = warp_max(amax);
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    amax = 0.f;
+    for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) amax = fmaxf(amax, s_max[w]);
+    const float block_scale = 127.0f / amax;
+    for (int i = threadIdx.x; i < K; i += blockDim.x)
+        q[off + i] = (uint8_t)(128.f + nearbyintf(to_f32<T>(x[off + i]) * block_scale));
+    if (threadIdx.x == 0) scale[blockIdx.x] = amax / 127.0f;
+}
+
 }  // namespace zl
 
 using namespace zl;
+
+extern "C" int zl_int8_quant_rows_u8(const void* x, void* q, float* scale, int M, int K, int dtype, zl_stream_t stream) {
+    ZL_CHECK_ARG(x && q && scale && M > 0 && K > 0);
+    ZL_CHECK_SUPPORTED(dtype == ZL_F16 || dtype == ZL_BF16);
+    const int threads = K >= 1024 ? 1024 : ((K + 31) / 32) * 32;
+    if (dtype == ZL_F16)
+        k_int8_quant_rows_u8<__half><<<M, threads, 0, stream>>>((const __half*)x, (uint8_t*)q, scale, K);
+    else
+        k_int8_quant_rows_u8<__nv_bfloat16><<<M, threads, 0, stream>>>((const __nv_bfloat16*)x, (uint8_t*)q, scale, K);
+    ZL_CHECK_LAUNCH();
+    return ZL_OK;
+}
 
 extern "C" int zl_kv_int8_quant_append(const void* k_src, const void* v_src, const int32_t* token_batch,
                                        const int32_t* placement, void* const* k_addrs, void* const* v_addrs,
