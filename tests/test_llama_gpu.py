@@ -208,8 +208,9 @@ def test_dual_stream_prefill_matches_single_stream(lib, cuda, monkeypatch, cfg):
         outs.append(steps)
     for a, b in zip(*outs):
         assert np.isfinite(a).all()
-        # M = 32 chunks vs two M = 16 halves run different GEMM kernels (fp16-HMMA vs exact-integer): fp16-level agreement
-        assert rel_l2(b, a) <= 3e-3
+        # M = 32 chunks (tcgen05 kernel: weights rounded to fp16, stand-alone RMSNorm) vs two M = 16 halves (exact-integer
+        # kernel, fused norm): fp16-level agreement
+        assert rel_l2(b, a) <= 5e-3
     orc = omodel.OracleLlama(cfg, sd, 5, 128, False, "f16", fuse_norm=True)
     for p, t in enumerate(prompt[:int(os.environ.get("ZL_TEST_PROMPT", "84"))]):
         ref = orc.decode(np.array([t]), [p])

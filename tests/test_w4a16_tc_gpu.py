@@ -40,8 +40,8 @@ def _check_watchdog(lib):
 
 def test_route_selects_tcgen05(lib):
     assert lib.zl_w4_int_layout_route(1, 4096, 4096) == 3       # exact-integer mma.sync kernel
-    assert lib.zl_w4_int_layout_route(8, 4096, 4096) == 3
-    assert lib.zl_w4_int_layout_route(16, 1024, 4096) == 3
+    assert lib.zl_w4_int_layout_route(4, 4096, 4096) == 3
+    assert lib.zl_w4_int_layout_route(16, 512, 1024) == 3
     assert lib.zl_w4_int_layout_route(16, 4096, 4096) == 4      # 16 staged token rows of K = 4096 do not fit beside the rings
     assert lib.zl_w4_int_layout_route(17, 4096, 4096) == 4      # tcgen05
     assert lib.zl_w4_int_layout_route(32, 4096, 14336) == 4

@@ -186,16 +186,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_w4a16_tc(const __grid_constan
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::RS; ++i) {
             mbar_init(&raw_full[i], 1);
-            mbar_init(&raw_empty[i], kTcDqThreads);
+            mbar_init(&raw_empty[i], kTcDqWarps);
         }
         for (int i = 0; i < C::AS; ++i) {
-            mbar_init(&a_full[i], kTcDqThreads);
+            mbar_init(&a_full[i], kTcDqWarps);
             mbar_init(&x_full[i], 1);
             mbar_init(&ax_empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 128);
+            mbar_init(&acc_empty[i], 4);
         }
         mbar_fence_init();
     }
@@ -314,13 +314,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_w4a16_tc(const __grid_constan
             const int split = it % S;
             const int g0 = (split * G) / S, g1 = ((split + 1) * G) / S;
             for (int gi = g0; gi < g1; ++gi) {
-                mbar_wait_wd(&raw_full[rs], rph, p.err, 0x600 + rs);
+                // one lane polls, the warp follows: 256 pollers on one mbarrier word cost more than the wait itself
+                if (lane == 0) mbar_wait_wd(&raw_full[rs], rph, p.err, 0x600 + rs);
+                __syncwarp();
                 const uint8_t* blk = smem + C::kRawOff + rs * kTcRawStage + blk_i * kW4BlockBytes;
                 const uint4 w0 = *reinterpret_cast<const uint4*>(blk + ((tt * 2 + 0) * 32 + lane) * 16);
                 const uint4 w1 = *reinterpret_cast<const uint4*>(blk + ((tt * 2 + 1) * 32 + lane) * 16);
                 const __half2 sc = *reinterpret_cast<const __half2*>(blk + kW4ScaleOff + (tt * 8 + g) * 4);
                 const int zz = blk[kW4ZeroOff + tt * 8 + g];
-                mbar_arrive(&raw_empty[rs]);
+                __syncwarp();                       // every lane's shared-memory reads of the stage have returned
+                if (lane == 0) mbar_arrive(&raw_empty[rs]);
                 if (++rs == C::RS) {
                     rs = 0;
                     rph ^= 1u;
@@ -328,7 +331,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_w4a16_tc(const __grid_constan
                 const __half2 c_lo = __float2half2_rn((float)(1024 + (zz & 0xF)));
                 const __half2 c_hi = __float2half2_rn((float)(64 + (zz >> 4)));
                 const __half2 s_lo = __half2half2(__low2half(sc)), s_hi = __half2half2(__high2half(sc));
-                mbar_wait_wd(&ax_empty[as], aph ^ 1u, p.err, 0x700 + as);
+                if (lane == 0) mbar_wait_wd(&ax_empty[as], aph ^ 1u, p.err, 0x700 + as);
+                __syncwarp();
                 uint8_t* a_st = smem + C::kAOff + as * kTcAStage + ka_off;
                 const uint32_t words[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
@@ -341,7 +345,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_w4a16_tc(const __grid_constan
                     *reinterpret_cast<uint4*>(a_st + row_off_hi + chunk) = make_uint4(hi0[0], hi0[1], hi1[0], hi1[1]);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor core
-                mbar_arrive(&a_full[as]);
+                __syncwarp();                       // all 32 lanes have fenced their stores; one arrival per warp
+                if (lane == 0) mbar_arrive(&a_full[as]);
                 if (++as == C::AS) {
                     as = 0;
                     aph ^= 1u;
@@ -359,7 +364,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_w4a16_tc(const __grid_constan
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
             const int tile = it / S, split = it % S;
             const int prow = tile * kTcRows + m;
-            mbar_wait_wd(&acc_full[acc], acc_ph, p.err, 0x800 + acc);
+            if (lane == 0) mbar_wait_wd(&acc_full[acc], acc_ph, p.err, 0x800 + acc);
+            __syncwarp();
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NTOK);
             float* wsp = (S > 1) ? p.ws + ((size_t)(tile * S + split) * p.M) * kTcRows + m : nullptr;
@@ -377,7 +383,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_w4a16_tc(const __grid_constan
                 }
             }
             tc_fence_before();
-            mbar_arrive(&acc_empty[acc]);
+            __syncwarp();                           // one arrival per epilogue warp
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
             if (++acc == 2) {
                 acc = 0;
                 acc_ph ^= 1u;

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kW8TcThreads, 1) k_w8a8_tc(const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 128);
+            mbar_init(&acc_empty[i], 4);
         }
         mbar_fence_init();
     }
@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(kW8TcThreads, 1) k_w8a8_tc(const __grid_consta
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
             const int tile = it / S, split = it % S;
             const int row = tile * kTcRows + m;
-            mbar_wait_wd(&acc_full[acc], acc_ph, p.err, 0x1800 + acc);
+            if (lane == 0) mbar_wait_wd(&acc_full[acc], acc_ph, p.err, 0x1800 + acc);
+            __syncwarp();
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NTOK);
             float* wsp = (S > 1) ? p.ws + ((size_t)(tile * S + split) * p.M) * kTcRows + m : nullptr;
@@ -221,7 +222,8 @@ __global__ void __launch_bounds__(kW8TcThreads, 1) k_w8a8_tc(const __grid_consta
                 }
             }
             tc_fence_before();
-            mbar_arrive(&acc_empty[acc]);
+            __syncwarp();                           // one arrival per epilogue warp
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
             if (++acc == 2) {
                 acc = 0;
                 acc_ph ^= 1u;
