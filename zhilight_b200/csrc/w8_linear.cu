@@ -15,6 +15,8 @@
 // Small N is covered by splitting K across the warps of a CTA (int32 partial sums add exactly).
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace zl {
 // tcgen05 W8A8 kernel (w8_tc.cu)
 bool w8_tc_supports(int N, int K);
@@ -440,7 +442,11 @@ extern "C" int zl_w8a8_gemm(const void* xq, const float* x_scale, const void* w,
     const uint8_t* xq8 = static_cast<const uint8_t*>(xq);
     const uint8_t* w8 = static_cast<const uint8_t*>(w);
     const int sw_f32 = kind == ZL_W8_FP8_ROWS ? 2 : (w_scale_dtype == ZL_F32 ? 1 : 0);
-    if (w8_tc_supports(N, K)) {
+    // measured on B200 (tools/w8_bench.py): with the reference's row-major (N, K) layout every 128-byte row segment of a TMA
+    // box comes from a different DRAM page, and the mma.sync kernel's 16-byte row-contiguous loads stream faster at decode
+    // sizes; the tcgen05 kernel takes over where the mma.sync kernel would re-stream the weights (M > 32: prefill chunks)
+    static const int tc_min_m = getenv("ZL_W8_TC_MIN_M") ? atoi(getenv("ZL_W8_TC_MIN_M")) : 33;
+    if (M >= tc_min_m && w8_tc_supports(N, K)) {
         // tcgen05 path (w8_tc.cu): both operands through the TMA engine, s32 / f32 accumulators in TMEM
         {
             static bool prepared[64] = {};
