@@ -420,6 +420,11 @@ def main():
     ms_dev, clocks = measure_decode(dec, B, args.steps, W, stream, barrier, sampler_gpu=local_rank)
     weight_bytes, kernels_per_step = dec.stats(B)
 
+    # sanity of the synthetic model: the logits of the last timed step must be finite (a NaN step costs the same time)
+    tok, pos = dec.get_state(B)
+    _, chk_logits = dec.decode(tok, pos, want_logits=True)
+    logits_finite = bool(np.isfinite(chk_logits).all())
+
     # ---- e2e: host buffers in/out every step ----
     tok, pos = dec.get_state(B)
     for _ in range(W):
@@ -451,7 +456,7 @@ def main():
         "warmup": W, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": {"int8": "int8 x int8 -> int32 (W8A8), f16 activations", "fp8": "e4m3 x e4m3 -> f32 (W8A8), f16 activations"}.get(
             args.quant, "bf16" if dense else "f16 (W4A16: int4 weights, fp16 activations, fp32 accumulate)"),
-        "data": "synthetic",
+        "data": "synthetic (random-init HF-GPTQ tensors: uniform nibbles recentred on the symmetric zero point, scales 0.002-0.006)",
         "config": {"workload": workload, "parallelism": "single GPU" if world == 1 else "tp%d (NVLink peer-memory exchange fused into the GEMMs, %s payload)" % (world, "int8-g32 (stand-alone kernel)" if args.tp_int8 else "fp16"),
                    "l2": "weights per step (%.2f GB) exceed L2 (126 MB); no explicit flush" % (weight_bytes / 1e9),
                    "pdl": not args.no_pdl, "cuda_graph": not args.no_graph, "fuse": args.fuse},
@@ -460,6 +465,7 @@ def main():
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(kernels_per_step) * args.steps if kernels_per_step else int(dec.lib.zl_launch_count(0) - launches0),
         "kernels_per_step": kernels_per_step,
+        "logits_finite": logits_finite,
         "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_roof, "peak": peak, "unit": "GB/s",
                           "frac": step_roof / peak},
     }

@@ -177,6 +177,17 @@ __global__ void k_and_u32(uint32_t* __restrict__ p, size_t n, uint32_t mask) {
     if (i < n) p[i] &= mask;
 }
 __global__ void k_set_f32(float* p, float v) { *p = v; }
+// synthetic symmetric checkpoints: a uniformly random nibble minus the fixed zero point 8 has mean -0.5, and with thousands
+// of such weights per row every layer adds a common-mode offset to the residual stream that overflows fp16 after ~30
+// layers (measured: NaN logits on the 32-layer model).  Nibble 0 -> 8 makes q - 8 symmetric around zero (-7 .. 7).
+__global__ void k_recentre_nibbles(uint32_t* __restrict__ p, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint32_t w = p[i];
+        const uint32_t zero = ~(w | (w >> 1) | (w >> 2) | (w >> 3)) & 0x11111111u;
+        p[i] = w | (zero << 3);
+    }
+}
 
 __global__ void k_iota(int32_t* p, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1193,6 +1204,12 @@ int stage_random_linear(zl_llama* m, const std::string& prefix, int K, int N, ui
     if (c.quant_type == 5) {
         const int G = K / c.group_size;
         RCHECK(stage_random(m, prefix + ".qweight", K / 8, N, 4, 0, 0, 0, seed));
+        if (c.sym) {
+            const size_t words = (size_t)(K / 8) * N;
+            k_recentre_nibbles<<<(unsigned)((words + 255) / 256), 256, 0, m->stream>>>(
+                static_cast<uint32_t*>(m->staged[prefix + ".qweight"].ptr), words);
+            ZL_CHECK_LAUNCH();
+        }
         RCHECK(stage_random(m, prefix + ".qzeros", G, N / 8, 4, c.sym ? 1 : 0, 0, 0, seed));
         RCHECK(stage_random(m, prefix + ".scales", G, N, 2, 2, 0.002f, 0.006f, seed));
     } else if (c.quant_type == 6) {

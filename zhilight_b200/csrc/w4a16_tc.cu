@@ -186,10 +186,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_w4a16_tc(const __grid_constan
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::RS; ++i) {
             mbar_init(&raw_full[i], 1);
-            mbar_init(&raw_empty[i], kTcDqWarps);
+            mbar_init(&raw_empty[i], kTcDqWarps / 2);
         }
         for (int i = 0; i < C::AS; ++i) {
-            mbar_init(&a_full[i], kTcDqWarps);
+            mbar_init(&a_full[i], kTcDqWarps / 2);
             mbar_init(&x_full[i], 1);
             mbar_init(&ax_empty[i], 1);
         }
@@ -299,58 +299,72 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_w4a16_tc(const __grid_constan
         }
     } else if (warp < kTcWarpEpi0) {
         // ---------------- dequant: raw int4 blocks -> fp16 A operand (K-major, 128-byte swizzle) ----------------
+        // Two groups of four warps take the stages alternately (group = stage parity): while one group sits in its proxy
+        // fence / barrier round trip, the other one is converting -- measured with ncu (profiles/r02_w4a16_tc_*): with all
+        // eight warps on the same stage the SM idled through every fence and MMA hand-over.  Inside a group warp w owns
+        // the 32-row block w of the stage (rows 32 w .. 32 w + 31, all 128 k).
         const int dw = warp - kTcWarpDq0;
-        const int blk_i = dw >> 1, tt = dw & 1;
+        const int grp = dw >> 2, blk_i = dw & 3;
         const int g = lane >> 2, t = lane & 3;
-        // rows tt*16 + g and + 8 of block blk_i; 16-byte chunk index inside the 128-k group: kc = 4 t + j
-        const int r_lo = blk_i * 32 + tt * 16 + g;
-        const uint32_t row_off_lo = (uint32_t)(r_lo >> 3) * 1024u + (uint32_t)(r_lo & 7) * 128u;
-        const uint32_t row_off_hi = row_off_lo + 1024u;   // row + 8: next 8-row group, same row-in-group
         const uint32_t ka_off = (uint32_t)(t >> 1) * (kTcRows * 128);
+        // lanes t and t ^ 2 of a quarter-warp write the same chunk column of the two k atoms: they walk the k-steps in a
+        // different order (j ^ 2 for t >= 2) so that one STS.128 wavefront never hits a bank twice
+        const int hx = t >> 1;             // which uint4 (hh) this lane converts first
         const int c_base = (t & 1) * 4;
-        int rs = 0, as = 0;
-        uint32_t rph = 0, aph = 0;
+        int stage = 0;                     // running stage counter of the CTA (all items)
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
             const int split = it % S;
             const int g0 = (split * G) / S, g1 = ((split + 1) * G) / S;
-            for (int gi = g0; gi < g1; ++gi) {
-                // one lane polls, the warp follows: 256 pollers on one mbarrier word cost more than the wait itself
+            for (int gi = g0; gi < g1; ++gi, ++stage) {
+                if ((stage & 1) != grp) continue;
+                const int rs = stage % C::RS, as = stage % C::AS;
+                const uint32_t rph = (uint32_t)(stage / C::RS) & 1u, aph = (uint32_t)(stage / C::AS) & 1u;
+                // one lane polls, the warp follows
                 if (lane == 0) mbar_wait_wd(&raw_full[rs], rph, p.err, 0x600 + rs);
                 __syncwarp();
                 const uint8_t* blk = smem + C::kRawOff + rs * kTcRawStage + blk_i * kW4BlockBytes;
-                const uint4 w0 = *reinterpret_cast<const uint4*>(blk + ((tt * 2 + 0) * 32 + lane) * 16);
-                const uint4 w1 = *reinterpret_cast<const uint4*>(blk + ((tt * 2 + 1) * 32 + lane) * 16);
-                const __half2 sc = *reinterpret_cast<const __half2*>(blk + kW4ScaleOff + (tt * 8 + g) * 4);
-                const int zz = blk[kW4ZeroOff + tt * 8 + g];
+                uint4 wv[2][2];            // [tt][first / second k-half in this lane's order]
+                __half2 sc[2];
+                int zz[2];
+#pragma unroll
+                for (int tt = 0; tt < 2; ++tt) {
+                    wv[tt][0] = *reinterpret_cast<const uint4*>(blk + ((tt * 2 + hx) * 32 + lane) * 16);
+                    wv[tt][1] = *reinterpret_cast<const uint4*>(blk + ((tt * 2 + (hx ^ 1)) * 32 + lane) * 16);
+                    sc[tt] = *reinterpret_cast<const __half2*>(blk + kW4ScaleOff + (tt * 8 + g) * 4);
+                    zz[tt] = blk[kW4ZeroOff + tt * 8 + g];
+                }
                 __syncwarp();                       // every lane's shared-memory reads of the stage have returned
                 if (lane == 0) mbar_arrive(&raw_empty[rs]);
-                if (++rs == C::RS) {
-                    rs = 0;
-                    rph ^= 1u;
-                }
-                const __half2 c_lo = __float2half2_rn((float)(1024 + (zz & 0xF)));
-                const __half2 c_hi = __float2half2_rn((float)(64 + (zz >> 4)));
-                const __half2 s_lo = __half2half2(__low2half(sc)), s_hi = __half2half2(__high2half(sc));
                 if (lane == 0) mbar_wait_wd(&ax_empty[as], aph ^ 1u, p.err, 0x700 + as);
                 __syncwarp();
                 uint8_t* a_st = smem + C::kAOff + as * kTcAStage + ka_off;
-                const uint32_t words[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {   // k-step j: words 2j (k + 0..3) and 2j + 1 (k + 4..7)
-                    uint32_t lo0[2], hi0[2], lo1[2], hi1[2];
-                    tc_dequant_word(words[2 * j], c_lo, s_lo, c_hi, s_hi, lo0, hi0);
-                    tc_dequant_word(words[2 * j + 1], c_lo, s_lo, c_hi, s_hi, lo1, hi1);
-                    const uint32_t chunk = (uint32_t)(((c_base + j) ^ g) << 4);   // swizzle: chunk ^ (row % 8)
-                    *reinterpret_cast<uint4*>(a_st + row_off_lo + chunk) = make_uint4(lo0[0], lo0[1], lo1[0], lo1[1]);
-                    *reinterpret_cast<uint4*>(a_st + row_off_hi + chunk) = make_uint4(hi0[0], hi0[1], hi1[0], hi1[1]);
+                for (int tt = 0; tt < 2; ++tt) {
+                    const __half2 c_lo = __float2half2_rn((float)(1024 + (zz[tt] & 0xF)));
+                    const __half2 c_hi = __float2half2_rn((float)(64 + (zz[tt] >> 4)));
+                    const __half2 s_lo = __half2half2(__low2half(sc[tt])), s_hi = __half2half2(__high2half(sc[tt]));
+                    // rows 32 blk + 16 tt + g (low nibbles) and + 8 (high nibbles): 8-row groups 4 blk + 2 tt and + 1
+                    const uint32_t row_lo = (uint32_t)(blk_i * 4 + tt * 2) * 1024u + (uint32_t)g * 128u;
+                    const uint32_t row_hi = row_lo + 1024u;
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const uint4 w = wv[tt][hh];
+                        const int j0 = ((hh ^ hx) << 1);          // k-steps 2 (hh ^ hx) and + 1 of the 128-k group
+                        const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                        for (int jj = 0; jj < 2; ++jj) {
+                            uint32_t lo0[2], hi0[2], lo1[2], hi1[2];
+                            tc_dequant_word(words[2 * jj], c_lo, s_lo, c_hi, s_hi, lo0, hi0);
+                            tc_dequant_word(words[2 * jj + 1], c_lo, s_lo, c_hi, s_hi, lo1, hi1);
+                            const uint32_t chunk = (uint32_t)(((c_base + j0 + jj) ^ g) << 4);   // swizzle: chunk ^ (row % 8)
+                            *reinterpret_cast<uint4*>(a_st + row_lo + chunk) = make_uint4(lo0[0], lo0[1], lo1[0], lo1[1]);
+                            *reinterpret_cast<uint4*>(a_st + row_hi + chunk) = make_uint4(hi0[0], hi0[1], hi1[0], hi1[1]);
+                        }
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor core
                 __syncwarp();                       // all 32 lanes have fenced their stores; one arrival per warp
                 if (lane == 0) mbar_arrive(&a_full[as]);
-                if (++as == C::AS) {
-                    as = 0;
-                    aph ^= 1u;
-                }
             }
         }
     } else {
