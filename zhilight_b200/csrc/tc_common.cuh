@@ -16,9 +16,12 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // bounded wait: a protocol bug must not hang the GPU (2 s, then the watchdog code is published and the kernel traps)
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, unsigned* err, unsigned code) {
     if (mbar_try_wait(bar, parity)) return;
-    const unsigned long long t0 = globaltimer_ns();
+    // the spin itself touches nothing but the barrier (a %globaltimer read per poll costs hundreds of cycles of wake-up
+    // latency on every hand-over); the SM clock is sampled once per 2048 polls
+    const long long t0 = clock64();
+    unsigned spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (globaltimer_ns() - t0 > 2000000000ull) {
+        if ((++spins & 2047u) == 0 && clock64() - t0 > 4000000000ll) {
             if (err) atomicExch(err, code);
             __threadfence_system();
             __trap();
@@ -32,6 +35,31 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, "
+        "%4}], [%5], %6;" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_hint(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                                 uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, "
+        "%4, %5}], [%6], %7;" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+// registers -> TMEM: lane i of the warp writes r[0..15] to columns taddr.col .. +15 of TMEM lane (taddr.lane + i)
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -90,6 +118,23 @@ inline bool tc_make_map_2d(CUtensorMap* map, const void* base, CUtensorMapDataTy
     const cuuint32_t estr[2] = {1u, 1u};
     return enc(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// general tiled map: rank <= 5, dims / box fastest-first, strides (bytes) of dims 1 .. rank-1
+inline bool tc_make_map_nd(CUtensorMap* map, const void* base, CUtensorMapDataType dt, int rank, const uint64_t* dims,
+                           const uint64_t* strides, const uint32_t* box, CUtensorMapSwizzle swz) {
+    EncodeTiledFn enc = tc_encode_fn();
+    if (!enc || rank < 1 || rank > 5) return false;
+    cuuint64_t gdim[5], gstride[4];
+    cuuint32_t b[5], estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        b[i] = box[i];
+        estr[i] = 1u;
+        if (i > 0) gstride[i - 1] = strides[i - 1];
+    }
+    return enc(map, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstride, b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // per-device scratch of the split-k reductions: fp32 / int32 partial tiles, arrival counters, watchdog word

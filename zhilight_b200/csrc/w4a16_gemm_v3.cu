@@ -147,9 +147,12 @@ __device__ __forceinline__ void pack_blocks(const W4Params& p, const uint8_t* ri
 // 16-bit activation mantissas share ONE IMMA: column 2i carries token i's high digit, column 2i+1 its low digit, both
 // signed (m = 256*hi' + lo', lo' = int8(m & 0xff), hi' = (m + 128) >> 8, |m| <= 2^14).  Half the IMMAs, half the B
 // loads, and the per-group int->float epilogue only touches real tokens.
-template <int NT, bool NORM, int WARPS, int SUBS, int STAGES, int RT = NT * 8, bool PACK = false>
+template <int NT, bool NORM, int WARPS, int SUBS, int STAGES, int RT = NT * 8, bool PACK = false, bool TPX = false>
 __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Params p) {
     using S = V3Smem<NT, WARPS, SUBS, STAGES, RT>;
+    // the tensor-parallel exchange code is compiled only into the TPX instantiations: carried as a run-time branch it cost
+    // every launch 10-20 registers (to the 128-register cap of the 512-thread CTA) and ~5 % of a single-GPU decode step
+    const int tp_mode = TPX ? p.tp_mode : 0;
     constexpr int WT = WARPS * SUBS;
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
     const uint8_t* tp_slots = nullptr;   // [ws][slot_bytes] of the exchange's parity
     size_t tp_slot_bytes = 0;
     int tp_ws = 0;
-    if (p.tp_mode == 1) {
+    if (tp_mode == 1) {
         const unsigned long long ep = *reinterpret_cast<volatile unsigned long long*>(tp->epoch);
         tp_ws = tp->ws;
         tp_slot_bytes = tp->slot_bytes;
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
             const int gi = warp + gl * WT;
             if (gi < G) raw[gl] = ld_cg_u2(p.x + (size_t)tok * p.ldx + gi * kW4GroupK + lane * 4);
         }
-        if (p.tp_mode == 1) {
+        if (tp_mode == 1) {
             // x := T(T(sum_r partial_r) + x): fp32 sum in rank order (identical on every rank and CTA), the reference's
             // reduce_sum + element_add_scale rounding points (model_context.cpp:203-243, block_kernel.cu:7-17)
             float acc[kMaxNg][4];
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
     int tp_push_ws = 0;
     unsigned long long tp_epoch = 0;
     size_t tp_my_slot = 0;
-    if (p.tp_mode == 2) {
+    if (tp_mode == 2) {
         tp_epoch = *reinterpret_cast<volatile unsigned long long*>(tp->epoch);
         tp_push_ws = tp->ws;
         tp_my_slot = ((size_t)(tp_epoch & 1ull) * tp->ws + tp->rank) * tp->slot_bytes;
@@ -636,7 +639,7 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
                 v += s_poison[tok];
                 if (p.bias) v += __half2float(p.bias[n0 + row]);
                 __half h = __float2half_rn(v);
-                if (p.tp_mode == 2) {   // partial sum of a row-parallel GEMM: straight into every rank's inbox (own slot too)
+                if (tp_mode == 2) {   // partial sum of a row-parallel GEMM: straight into every rank's inbox (own slot too)
                     for (int r = 0; r < tp_push_ws; ++r)
                         reinterpret_cast<__half*>(tp->inbox[r] + tp_my_slot)[(size_t)tok * p.N + n0 + row] = h;
                     continue;
@@ -649,7 +652,7 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
         if (S::kRedBufs == 1) sub_barrier(1 + sub, WARPS * 32);
         stamp();
     }
-    if (p.tp_mode == 2) {
+    if (tp_mode == 2) {
         // every store of this CTA is fenced to system scope, then the last CTA of the grid publishes the flags: the peers'
         // next GEMM (reduce-in above) acquires them.  Advancing the local epoch tells the local consumer which exchange
         // to wait for.
@@ -680,6 +683,15 @@ static cudaError_t launch_v3_t(const W4Params& p, int smem, bool pdl, cudaStream
     const int tiles = p.N / 32;
     const int want = (tiles + SUBS - 1) / SUBS;
     const int grid = want < v3_num_sms() ? want : v3_num_sms();
+    if (p.tp_mode != 0) {
+        // exchange variants exist for the 4-stage rings only (launch_w4_v3 routes tensor-parallel launches there)
+        if constexpr (STAGES == 4 && RT == NT * 8) {
+            return launch(k_w4a16_v3<NT, NORM, WARPS, SUBS, STAGES, RT, PACK, true>, dim3(grid), dim3(WARPS * SUBS * 32),
+                          (size_t)smem, stream, pdl, p);
+        } else {
+            return cudaErrorNotSupported;
+        }
+    }
     return launch(k_w4a16_v3<NT, NORM, WARPS, SUBS, STAGES, RT, PACK>, dim3(grid), dim3(WARPS * SUBS * 32), (size_t)smem, stream,
                   pdl, p);
 }
@@ -725,6 +737,17 @@ static bool v3_is_tall(const W4Params& p) {
 // returns false when the staged activations do not fit shared memory (caller falls back to the fp16 kernels)
 bool launch_w4_v3(const W4Params& p, bool pdl, cudaStream_t stream, cudaError_t* err) {
     const bool tall = v3_is_tall(p);
+    if (p.tp_mode != 0) {   // fused tensor-parallel exchange: 4-stage variants
+        if (p.mc <= 8) {
+            if (tall && v3_try<1, 16, 1, 4>(p, pdl, stream, err)) return true;
+            return v3_try<1, 8, 2, 4>(p, pdl, stream, err);
+        }
+        if (p.mc <= 16) {
+            if (tall && v3_try<2, 16, 1, 4>(p, pdl, stream, err)) return true;
+            return v3_try<2, 8, 2, 4>(p, pdl, stream, err);
+        }
+        return false;
+    }
     if (p.mc <= 2) {   // deepest ring that fits (reduction buffers shrunk to 2 token rows)
         const int ms = v3_max_stages();
         if (tall) {
@@ -780,6 +803,14 @@ cudaError_t prepare_w4_v3() {
     ZL_SET(1, false, 16, 1, 4) ZL_SET(1, true, 16, 1, 4)
     ZL_SET(2, false, 8, 2, 4) ZL_SET(2, true, 8, 2, 4) ZL_SET(2, false, 16, 1, 4) ZL_SET(2, true, 16, 1, 4)
 #undef ZL_SET
+#define ZL_SETX(NT, NORM, W, SB, PK)                                                                            \
+    e = cudaFuncSetAttribute(k_w4a16_v3<NT, NORM, W, SB, 4, NT * 8, PK, true>,                                  \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, kV3Budget);                           \
+    if (e != cudaSuccess) return e;
+    ZL_SETX(1, false, 8, 2, false) ZL_SETX(1, true, 8, 2, false) ZL_SETX(1, false, 16, 1, false) ZL_SETX(1, true, 16, 1, false)
+    ZL_SETX(1, false, 8, 2, true) ZL_SETX(1, true, 8, 2, true) ZL_SETX(1, false, 16, 1, true) ZL_SETX(1, true, 16, 1, true)
+    ZL_SETX(2, false, 8, 2, false) ZL_SETX(2, true, 8, 2, false) ZL_SETX(2, false, 16, 1, false) ZL_SETX(2, true, 16, 1, false)
+#undef ZL_SETX
     return cudaSuccess;
 }
 

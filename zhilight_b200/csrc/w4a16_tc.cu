@@ -50,11 +50,14 @@ struct TcCfg {
 
 struct alignas(64) W4TcParams {
     CUtensorMap xmap;           // x (M, K) fp16 row-major, box {64, NTOK}, 128-byte swizzle
+    CUtensorMap wmap;           // TS kernel: ZLW4I nibble words as [N/32][G][32 rows][64 B], box {64 B, 32, 1, 4}, 64-byte swizzle
+    CUtensorMap tmap;           // TS kernel: the 80-byte scale / zero trailers as [N/32][G][80 B], box {80 B, 1, 4}
     const uint8_t* packed;      // ZLW4I
     const __half* bias;         // indexed by PACKED row
     const __half* residual;
     __half* y;
     int M, N, K, epi, S;        // S = k splits
+    int dbg;                    // ZL_TC_DBG timing ablations of the TS kernel (results are wrong): 1 no x loads, 2 no dequant, 4 no MMA, 8 no weight loads
     float* ws;                  // [tile][split][M][128] fp32 partial sums (S > 1)
     unsigned* counters;         // [tile] arrivals (S > 1), left at zero
     unsigned* err;              // watchdog code
@@ -440,6 +443,334 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_w4a16_tc(const __grid_constan
     }
 }
 
+// =======================================================================================================================
+// TS variant: the A operand (dequantised weights) lives in TENSOR MEMORY, not in shared memory.
+//
+// Why (measured on the SS kernel above, profiles/r02_w4a16_tc_*): a 128 x 128 fp16 A stage is 32 KB that the dequant warps
+// write to shared memory and the tensor core reads back -- 64 KB of shared-memory traffic per 8.5 KB of HBM traffic, above
+// the 128 B/clk the SM has at the HBM rate -- plus a generic->async proxy fence per hand-over and ~10 address / store
+// instructions per converted word.  tcgen05.mma takes A from TMEM: TMEM lane = weight row, 32-bit column = two consecutive
+// k, so a dequant thread that owns ONE ROW converts its nibbles in registers and hands them over with tcgen05.st -- no
+// shared-memory round trip, no swizzle arithmetic, no proxy fence.
+//
+//   warps 0-3          epilogue   (TMEM lane quadrant = warp)
+//   warps 4 .. 4+4KQ-1 dequant    (quadrant = warp % 4 = 32-row block of the tile; k-slice = (warp - 4) / 4 of KQ)
+//   then               raw producer (tensor-TMA, see below), x producer, MMA issuer (+ TMEM alloc)
+//
+// A ZLW4I word holds 4 k of row g (low nibbles) and of row g + 8 (high nibbles); the thread of row g masks the low
+// nibbles, the thread of row g + 8 the high ones (same words, a shared-memory broadcast).  Lanes g = 0..7 of a
+// quarter-warp read 16-byte chunks 64 B apart -- a 4-way bank conflict in the plain record layout -- so the nibble words
+// arrive through a tensor map with 64-byte swizzle (chunk ^= (row >> 1) & 3): conflict-free, the HBM format is unchanged.
+// The 80-byte scale / zero trailers of the four blocks of a stage come through a second (unswizzled) map.
+template <int NTOK>
+struct TsCfg {
+    static constexpr int KQ = 2;                                        // k-slices per quadrant (dequant warps = 4 KQ)
+    static constexpr int DQ = 4 * KQ;
+    static constexpr int kWarpDq0 = 4, kWarpRaw = 4 + DQ, kWarpX = kWarpRaw + 1, kWarpMma = kWarpRaw + 2;
+    static constexpr int kThreads = (kWarpMma + 1) * 32;
+    static constexpr int AS = NTOK <= 128 ? 4 : 3;                      // A (TMEM) / x (smem) stages
+    static constexpr int RS = NTOK <= 128 ? 4 : 3;                      // raw weight stages
+    static constexpr int NACC = NTOK <= 128 ? 2 : 1;                    // accumulator buffers in TMEM
+    static constexpr int kACol0 = NACC * NTOK;                          // first A column; 64 columns per stage
+    static constexpr int kXStage = 2 * NTOK * 128;
+    static constexpr int kNibStage = 4 * 2048, kTrStage = 384;          // 4 x 80 B trailers, padded to the TMA alignment
+    static constexpr int kXOff = 0;
+    static constexpr int kNibOff = kXOff + AS * kXStage;
+    static constexpr int kTrOff = kNibOff + RS * kNibStage;
+    static constexpr int kBarOff = kTrOff + RS * kTrStage;
+    static constexpr int kNumBars = 2 * RS + 3 * AS + 4;
+    static constexpr int kMiscOff = kBarOff + kNumBars * 8;
+    static constexpr int kBytes = kMiscOff + 16 + 1024;
+    static_assert(kACol0 + AS * 64 <= 512, "TMEM columns");
+};
+
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+
+template <int NTOK>
+__global__ void __launch_bounds__(TsCfg<NTOK>::kThreads, 1) k_w4a16_ts(const __grid_constant__ W4TcParams p) {
+    using C = TsCfg<NTOK>;
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBarOff);
+    uint64_t* raw_full = bars;
+    uint64_t* raw_empty = raw_full + C::RS;
+    uint64_t* a_full = raw_empty + C::RS;
+    uint64_t* x_full = a_full + C::AS;
+    uint64_t* ax_empty = x_full + C::AS;
+    uint64_t* acc_full = ax_empty + C::AS;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + C::kMiscOff);
+    uint32_t* s_last = s_tmem + 1;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = p.K / kW4GroupK, n_tiles = p.N / kTcRows, S = p.S;
+    const int n_items = n_tiles * S;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < C::RS; ++i) {
+            mbar_init(&raw_full[i], 1);
+            mbar_init(&raw_empty[i], C::DQ);
+        }
+        for (int i = 0; i < C::AS; ++i) {
+            mbar_init(&a_full[i], C::DQ);
+            mbar_init(&x_full[i], 1);
+            mbar_init(&ax_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == C::kWarpMma) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    pdl_trigger();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == C::kWarpRaw) {
+        // ---------------- weight stream: constants, may run ahead of the predecessor kernel (PDL) ----------------
+        if (lane == 0) {
+            const uint64_t pol = l2_evict_first_policy();
+            int rs = 0;
+            uint32_t ph = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                const int tile = it / S, split = it % S;
+                const int g0 = (split * G) / S, g1 = ((split + 1) * G) / S;
+                for (int gi = g0; gi < g1; ++gi) {
+                    mbar_wait_wd(&raw_empty[rs], ph ^ 1u, p.err, 0x100 + rs);
+                    if (p.dbg & 8) {
+                        mbar_arrive(&raw_full[rs]);
+                    } else {
+                        mbar_expect_tx(&raw_full[rs], C::kNibStage + 4 * 80);
+                        tma_load_4d_hint(smem + C::kNibOff + rs * C::kNibStage, &p.wmap, 0, 0, gi, tile * 4, &raw_full[rs], pol);
+                        tma_load_3d_hint(smem + C::kTrOff + rs * C::kTrStage, &p.tmap, 0, gi, tile * 4, &raw_full[rs], pol);
+                    }
+                    if (++rs == C::RS) {
+                        rs = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == C::kWarpX) {
+        // ---------------- activations: produced by the predecessor kernel ----------------
+        if (lane == 0) {
+            pdl_wait();
+            int as = 0;
+            uint32_t ph = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                const int split = it % S;
+                const int g0 = (split * G) / S, g1 = ((split + 1) * G) / S;
+                for (int gi = g0; gi < g1; ++gi) {
+                    mbar_wait_wd(&ax_empty[as], ph ^ 1u, p.err, 0x200 + as);
+                    if (p.dbg & 1) {
+                        mbar_arrive(&x_full[as]);
+                    } else {
+                        mbar_expect_tx(&x_full[as], C::kXStage);
+                        uint8_t* dst = smem + C::kXOff + as * C::kXStage;
+                        tma_load_2d(dst, &p.xmap, gi * kW4GroupK, 0, &x_full[as]);
+                        tma_load_2d(dst + NTOK * 128, &p.xmap, gi * kW4GroupK + 64, 0, &x_full[as]);
+                    }
+                    if (++as == C::AS) {
+                        as = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == C::kWarpMma) {
+        // ---------------- one thread issues every MMA of the CTA: A from TMEM, B (activations) from shared memory ----------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc_idesc_f16(NTOK);
+            int as = 0, acc = 0;
+            uint32_t ph = 0, acc_ph = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                const int split = it % S;
+                const int g0 = (split * G) / S, g1 = ((split + 1) * G) / S;
+                mbar_wait_wd(&acc_empty[acc], acc_ph ^ 1u, p.err, 0x300 + acc);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NTOK);
+                for (int gi = g0; gi < g1; ++gi) {
+                    mbar_wait_wd(&a_full[as], ph, p.err, 0x400 + as);
+                    mbar_wait_wd(&x_full[as], ph, p.err, 0x500 + as);
+                    tc_fence_after();
+                    const uint32_t a_col = tmem_base + (uint32_t)(C::kACol0 + as * 64);
+                    const uint32_t x_base = smem_u32(smem + C::kXOff + as * C::kXStage);
+                    if (!(p.dbg & 4) || gi == g0)
+#pragma unroll
+                    for (int ka = 0; ka < 2; ++ka) {
+                        const uint64_t xd = tc_desc_sw128(x_base + ka * (NTOK * 128));
+#pragma unroll
+                        for (int k16 = 0; k16 < 4; ++k16)   // 16 k = 8 TMEM columns of A, 32 bytes inside the swizzle atom of x
+                            tc_mma_f16_ts(d_tmem, a_col + (uint32_t)((ka * 4 + k16) * 8), xd + (uint64_t)(k16 * 2), idesc,
+                                          (gi > g0 || ka > 0 || k16 > 0) ? 1u : 0u);
+                    }
+                    tc_commit(&ax_empty[as]);   // frees the A columns and the x stage once the MMAs above have read them
+                    if (++as == C::AS) {
+                        as = 0;
+                        ph ^= 1u;
+                    }
+                }
+                tc_commit(&acc_full[acc]);
+                if (++acc == C::NACC) {
+                    acc = 0;
+                    acc_ph ^= 1u;
+                }
+            }
+        }
+    } else if (warp >= C::kWarpDq0) {
+        // ---------------- dequant: the lane owns packed row 32 q + lane of the tile, k-slice ks of every stage ----------------
+        const int q = warp & 3, ks = (warp - C::kWarpDq0) >> 2;
+        const int tt = lane >> 4, hi = (lane >> 3) & 1, g = lane & 7;
+        constexpr int KW = kW4GroupK / C::KQ;            // k per warp and stage: 64 (KQ = 2) or 32 (KQ = 4)
+        constexpr int NCH = KW / 16;                     // 16-k chunks (one uint4 each) per lane and stage
+        const uint32_t mask = hi ? 0xf0f0f0f0u : 0x0f0f0f0fu;
+        const uint32_t magic = hi ? 0x54545454u : 0x64646464u;   // 64 + n / 16 for a high nibble n, 1024 + n for a low one
+        const uint32_t sw = (uint32_t)(g >> 1) & 3u;     // the map's 64-byte swizzle: chunk ^= (row >> 1) & 3, row % 8 = g
+        const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(C::kACol0 + ks * (KW / 2));
+        int rs = 0, as = 0;
+        uint32_t rph = 0, aph = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            const int split = it % S;
+            const int g0 = (split * G) / S, g1 = ((split + 1) * G) / S;
+            for (int gi = g0; gi < g1; ++gi) {
+                if (lane == 0) mbar_wait_wd(&raw_full[rs], rph, p.err, 0x600 + rs);
+                __syncwarp();
+                const uint8_t* nib = smem + C::kNibOff + rs * C::kNibStage + q * 2048;
+                const uint8_t* tr = smem + C::kTrOff + rs * C::kTrStage + q * 80;
+                uint4 wv[NCH];
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    // 16-k chunk kc of the group: k = 32 t + 16 hh + ..., record row (2 tt + hh) * 8 + g, chunk t
+                    const int kc = ks * NCH + c, t = kc >> 1, hh = kc & 1;
+                    wv[c] = *reinterpret_cast<const uint4*>(nib + ((tt * 2 + hh) * 8 + g) * 64 + (((uint32_t)t ^ sw) << 4));
+                }
+                const __half2 sc2 = *reinterpret_cast<const __half2*>(tr + (tt * 8 + g) * 4);
+                const int zz = tr[64 + tt * 8 + g];
+                __syncwarp();                       // every lane's shared-memory reads of the stage have returned
+                if (lane == 0) mbar_arrive(&raw_empty[rs]);
+                const __half2 cz = __float2half2_rn(hi ? (float)(64 + (zz >> 4)) : (float)(1024 + (zz & 0xF)));
+                const __half2 s2 = hi ? __half2half2(__high2half(sc2)) : __half2half2(__low2half(sc2));
+                if (lane == 0) mbar_wait_wd(&ax_empty[as], aph ^ 1u, p.err, 0x700 + as);
+                __syncwarp();
+                tc_fence_after();
+                if (!(p.dbg & 2))
+#pragma unroll
+                for (int c2 = 0; c2 < NCH; c2 += 2) {   // 32 k = 16 columns per tcgen05.st
+                    uint32_t r[16];
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const uint32_t words[4] = {wv[c2 + c].x, wv[c2 + c].y, wv[c2 + c].z, wv[c2 + c].w};
+#pragma unroll
+                        for (int wq = 0; wq < 4; ++wq) {
+                            const uint32_t wm = words[wq] & mask;
+                            uint32_t a0 = __byte_perm(wm, magic, 0x4140), a1 = __byte_perm(wm, magic, 0x4342);
+                            __half2 v0 = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&a0), cz), s2);
+                            __half2 v1 = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&a1), cz), s2);
+                            r[c * 8 + wq * 2] = *reinterpret_cast<uint32_t*>(&v0);
+                            r[c * 8 + wq * 2 + 1] = *reinterpret_cast<uint32_t*>(&v1);
+                        }
+                    }
+                    tc_st16(lane_taddr + (uint32_t)(as * 64 + c2 * 8), r);
+                }
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();                       // one arrival per warp
+                if (lane == 0) mbar_arrive(&a_full[as]);
+                if (++rs == C::RS) {
+                    rs = 0;
+                    rph ^= 1u;
+                }
+                if (++as == C::AS) {
+                    as = 0;
+                    aph ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ---------------- epilogue: TMEM -> registers -> global ----------------
+        const int q = warp;                      // TMEM lane quadrant this warp may read
+        const int m = q * 32 + lane;             // row inside the tile
+        const int et = warp * 32 + lane;
+        pdl_wait();
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            const int tile = it / S, split = it % S;
+            const int prow = tile * kTcRows + m;
+            if (lane == 0) mbar_wait_wd(&acc_full[acc], acc_ph, p.err, 0x800 + acc);
+            __syncwarp();
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NTOK);
+            float* wsp = (S > 1) ? p.ws + ((size_t)(tile * S + split) * p.M) * kTcRows + m : nullptr;
+#pragma unroll 1
+            for (int c0 = 0; c0 < NTOK; c0 += 16) {
+                if (c0 >= p.M) break;
+                float v[16];
+                tc_ld16(taddr + (uint32_t)c0, v);
+                if (S > 1) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < p.M) __stcg(wsp + (size_t)(c0 + i) * kTcRows, v[i]);
+                } else {
+                    tc_epilogue16(p, prow, lane, c0, v);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();                           // one arrival per epilogue warp
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            if (++acc == C::NACC) {
+                acc = 0;
+                acc_ph ^= 1u;
+            }
+            if (S > 1) {
+                // the last CTA of the tile reduces the S partial sums in split order and runs the epilogue
+                __threadfence();
+                epi_bar();
+                if (et == 0) *s_last = (atomicAdd(&p.counters[tile], 1u) == (unsigned)(S - 1)) ? 1u : 0u;
+                epi_bar();
+                const bool last = *s_last != 0u;
+                epi_bar();   // s_last may be rewritten by the next item
+                if (last) {
+                    __threadfence();
+                    const float* base = p.ws + ((size_t)tile * S * p.M) * kTcRows + m;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < p.M; c0 += 16) {
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                        for (int s = 0; s < S; ++s) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (c0 + i < p.M) v[i] += __ldcg(base + ((size_t)s * p.M + c0 + i) * kTcRows);
+                        }
+                        tc_epilogue16(p, prow, lane, c0, v);
+                    }
+                    if (et == 0) p.counters[tile] = 0u;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == C::kWarpMma) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    }
+}
+
 // ---- host side --------------------------------------------------------------------------------------------------------
 static TcDeviceState g_tc_state[64];
 
@@ -467,6 +798,12 @@ cudaError_t prepare_w4_tc() {
         return e;
     ZL_TC_SET(32) ZL_TC_SET(64) ZL_TC_SET(128) ZL_TC_SET(256)
 #undef ZL_TC_SET
+#define ZL_TS_SET(NT)                                                                                             \
+    if ((e = cudaFuncSetAttribute(k_w4a16_ts<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
+                                  TsCfg<NT>::kBytes)) != cudaSuccess)                                              \
+        return e;
+    ZL_TS_SET(32) ZL_TS_SET(64) ZL_TS_SET(128) ZL_TS_SET(256)
+#undef ZL_TS_SET
     return cudaSuccess;
 }
 
@@ -533,6 +870,10 @@ cudaError_t launch_w4_tc(const W4Params& p, bool pdl, cudaStream_t stream) {
     q.N = p.N;
     q.K = p.K;
     q.epi = p.epi;
+    {
+        static const int tc_dbg = getenv("ZL_TC_DBG") ? atoi(getenv("ZL_TC_DBG")) : 0;
+        q.dbg = tc_dbg;
+    }
     const int n_tiles = p.N / kTcRows, G = p.K / kW4GroupK;
     const int forced = tc_force_splits();
     q.S = (forced > 0 && forced <= G) ? forced : tc_pick_splits(n_tiles, G, p.mc, st->ws_bytes);
@@ -552,6 +893,25 @@ cudaError_t launch_w4_tc(const W4Params& p, bool pdl, cudaStream_t stream) {
     q.dim_head = p.dim_head;
     const int items = n_tiles * q.S;
     const int sms = device_sm_count();
+    static const bool use_ss = getenv("ZL_W4_TC_SS") != nullptr;   // A/B: the shared-memory-A variant
+    if (!use_ss) {
+        const uint64_t nb = (uint64_t)p.N / 32;
+        const uint64_t wd[4] = {16, 32, (uint64_t)G, nb}, wstr[3] = {64, (uint64_t)kW4BlockBytes, (uint64_t)G * kW4BlockBytes};
+        const uint32_t wbox[4] = {16, 32, 1, 4};
+        const uint64_t td[3] = {20, (uint64_t)G, nb}, tstr[2] = {(uint64_t)kW4BlockBytes, (uint64_t)G * kW4BlockBytes};
+        const uint32_t tbox[3] = {20, 1, 4};
+        if (!tc_make_map_nd(&q.wmap, p.packed, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, wd, wstr, wbox, CU_TENSOR_MAP_SWIZZLE_64B) ||
+            !tc_make_map_nd(&q.tmap, p.packed + kW4ScaleOff, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, td, tstr, tbox,
+                            CU_TENSOR_MAP_SWIZZLE_NONE))
+            return cudaErrorInvalidValue;
+        const dim3 grid(items < sms ? items : sms);
+        switch (ntok) {
+            case 32: return launch(k_w4a16_ts<32>, grid, dim3(TsCfg<32>::kThreads), (size_t)TsCfg<32>::kBytes, stream, pdl, q);
+            case 64: return launch(k_w4a16_ts<64>, grid, dim3(TsCfg<64>::kThreads), (size_t)TsCfg<64>::kBytes, stream, pdl, q);
+            case 128: return launch(k_w4a16_ts<128>, grid, dim3(TsCfg<128>::kThreads), (size_t)TsCfg<128>::kBytes, stream, pdl, q);
+            default: return launch(k_w4a16_ts<256>, grid, dim3(TsCfg<256>::kThreads), (size_t)TsCfg<256>::kBytes, stream, pdl, q);
+        }
+    }
     const dim3 grid(items < sms ? items : sms), block(kTcThreads);
     switch (ntok) {
         case 32: return launch(k_w4a16_tc<32>, grid, block, (size_t)TcCfg<32>::kBytes, stream, pdl, q);
