@@ -142,8 +142,12 @@ int zl_w4_int_layout_route(int M, int N, int K);
 /* last watchdog code published by a tcgen05 kernel on the current device (0 = none); a bounded mbarrier wait that expires
  * records which pipeline barrier starved and traps instead of hanging the GPU. */
 unsigned zl_w4_tc_watchdog(void);
-/* debug / tests: force the k-split count of the tcgen05 kernel (0 = automatic; also ZL_TC_SPLITS). */
+/* debug / tests: at least `splits` pieces per weight-row tile in the tcgen05 kernel's stream-k schedule (0 = automatic; also
+ * ZL_TC_SPLITS). */
 int zl_w4_tc_set_splits(int splits);
+/* debug: with ZL_TC_DBG & 16, CTA 0 of the tcgen05 kernel stamps its pipeline hand-overs with clock64; copies
+ * [11 roles][64 stages][4 events] of the last launch to `out` (n <= 2816 values). */
+int zl_w4_tc_read_trace(long long* out, int n);
 /* debug: device buffer of grid*16 uint64 globaltimer samples written by the integer kernel (NULL = off). */
 int zl_w4_set_trace(void* buf);
 /* row_map (n_heads_total*dim_head) for zl_w4_pack so that RoPE partners (c, c+d/2) share an MMA tile. */

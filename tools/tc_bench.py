@@ -62,7 +62,7 @@ def bench(n, k, m, variant=1, graph=False):
 
 if __name__ == "__main__":
     if len(sys.argv) >= 5 and sys.argv[1] == "--one":
-        print(json.dumps(bench(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))), flush=True)
+        print(json.dumps(bench(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), graph="--graph" in sys.argv)), flush=True)
         sys.exit(0)
     graph = "--graph" in sys.argv
     for (n, k) in ((6144, 4096), (4096, 4096), (28672, 4096), (4096, 14336)):

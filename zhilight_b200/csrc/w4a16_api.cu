@@ -3,7 +3,7 @@
 // Stands in for nn::gptq::gptq_gemm_k_major's router (reference src/nn/quant/gptq/q_gemm_k_major.cu:957-1116:
 // M <= 40 GEMV, else dequant + cuBLASLt) and for GPTQMarlin::forward (src/nn/linear/linear.cpp:1247-1451):
 //   M <= 16 and the staged activations fit shared memory -> k_w4a16_v3  (exact-integer mma.sync kernel, ZLW4I layout)
-//   otherwise, N % 128 == 0                              -> k_w4a16_tc  (tcgen05 / TMEM / TMA kernel, ZLW4I layout)
+//   otherwise, N % 128 == 0                              -> k_w4a16_ts  (tcgen05 kernel, A operand in TMEM, ZLW4I layout)
 //   otherwise                                            -> k_w4a16_v2  (fp16 mma.sync kernel, ZLW4 layout, 32-row passes)
 #include "common.cuh"
 #include "w4_layout.cuh"
