@@ -28,17 +28,18 @@ for _ in range(3):
     ops.w4a16_gemm_fused(x, pack, n, k, out=out, variant=1)
 torch.cuda.synchronize()
 ROLES = 11
-buf = np.zeros(ROLES * 64 * 4, np.int64)
+buf = np.zeros(ROLES * 64 * 8, np.int64)
 lib.zl_w4_tc_read_trace.restype = ctypes.c_int
 rc = lib.zl_w4_tc_read_trace(buf.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)), buf.size)
 assert rc == 0, rc
-t = buf.reshape(ROLES, 64, 4)
+t = buf.reshape(ROLES, 64, 8)
 t0 = t[t > 0].min()
 r = lambda a: int(a - t0) if a > 0 else -1
-print("cycles since first stamp; raw: wait-start/got raw_empty | x: got ax_empty | dq0 (warp 4) / dq4 (warp 8): got raw_full, got ax_empty, "
-      "arrived a_full | slowest dq arrive | mma: start, got a_full, got x_full, committed")
-for s in range(40):
+print("cycles since first stamp (a stage = 2 quantisation groups for <= 128 tokens).  raw: got raw_empty | x: got ax_empty | dq (warp 4): "
+      "start, got raw_full, got ax_empty, arrived a_full | slowest dq arrive | mma: start, got a_full, issued + committed")
+for s in range(32):
     dq_arr = max(t[3 + w, s, 3] for w in range(8))
-    print("st %2d | raw %6d %6d | x %6d | dq0 %6d %6d %6d | dq4 %6d %6d %6d | dqmax %6d | mma %6d %6d %6d %6d" % (
-        s, r(t[0, s, 0]), r(t[0, s, 1]), r(t[1, s, 1]), r(t[3, s, 1]), r(t[3, s, 2]), r(t[3, s, 3]), r(t[7, s, 1]), r(t[7, s, 2]),
-        r(t[7, s, 3]), r(dq_arr), r(t[2, s, 0]), r(t[2, s, 1]), r(t[2, s, 2]), r(t[2, s, 3])))
+    d = t[3, s]
+    mm = t[2, s]
+    print("st %2d | raw %6d | x %6d | dq %6d %6d %6d %6d | dqmax %6d | mma %6d %6d %6d" % (
+        s, r(t[0, s, 1]), r(t[1, s, 1]), r(d[0]), r(d[1]), r(d[2]), r(d[3]), r(dq_arr), r(mm[0]), r(mm[1]), r(mm[3])))

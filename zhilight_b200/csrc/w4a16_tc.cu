@@ -58,7 +58,7 @@ struct alignas(64) W4TcParams {
     float* ws;                  // [2 * CTA + slot][M][128] fp32 partial tiles
     unsigned* counters;         // [tile] arrivals of the pieces of a shared tile, left at zero
     unsigned* err;              // watchdog code
-    long long* trace;           // ZL_TC_DBG & 16: clock64 stamps of CTA 0, [role 0..7][64 stages][4]
+    long long* trace;           // ZL_TC_DBG & 16: clock64 stamps of CTA 0, [role][64 stages][8]
     const float* cos;
     const float* sin;
     __half* q_out;
@@ -147,27 +147,32 @@ __device__ __forceinline__ void tc_epilogue16(const W4TcParams& p, int prow, int
 }
 
 
-template <int NTOK, int NG>
+template <int NTOK>
 struct TsCfg {
     static constexpr int KQ = 2;                                        // k-slices per quadrant
     static constexpr int GW = 4 * KQ;                                   // dequant warps per group (one group converts one stage)
-    static constexpr int DQ = NG * GW;                                  // NG groups take the stages round-robin
+    static constexpr int NG = 2;                                        // groups take the stages alternately
+    static constexpr int DQ = NG * GW;
     static constexpr int kWarpDq0 = 4, kWarpRaw = 4 + DQ, kWarpX = kWarpRaw + 1, kWarpMma = kWarpRaw + 2;
     static constexpr int kThreads = (kWarpMma + 1) * 32;
-    static constexpr int AS = NTOK <= 64 ? 6 : (NTOK <= 128 ? 4 : 3);   // A (TMEM) / x (smem) stages
-    static constexpr int RS = NTOK <= 64 ? 6 : (NTOK <= 128 ? 4 : 3);   // raw weight stages
+    // A pipeline stage is KG quantisation groups (KG x 128 k): every hand-over (mbarrier wait, fence, commit) costs the
+    // single MMA-issuing warp 60-150 cycles, ~700 per stage (measured with the clock64 trace, profiles/r02_tc_trace_*),
+    // against 128 cycles of tensor work per group at 32 tokens -- two groups per stage halve that overhead per byte.
+    static constexpr int KG = NTOK <= 128 ? 2 : 1;
+    static constexpr int AS = NTOK <= 64 ? 3 : (NTOK <= 128 ? 2 : 3);   // A (TMEM) / x (smem) stages
+    static constexpr int RS = NTOK <= 64 ? 4 : 3;                       // raw weight stages
     static constexpr int NACC = NTOK <= 128 ? 2 : 1;                    // accumulator buffers in TMEM
-    static constexpr int kACol0 = NACC * NTOK;                          // first A column; 64 columns per stage
-    static constexpr int kXStage = 2 * NTOK * 128;                      // [k atom (64 k)][token][128 B]
-    static constexpr int kNibStage = 4 * 2048, kTrStage = 384;          // 4 x 80 B trailers, padded to the TMA alignment
+    static constexpr int kACol0 = NACC * NTOK;                          // first A column; 64 columns per group
+    static constexpr int kXGroup = 2 * NTOK * 128;                      // [k atom (64 k)][token][128 B]
+    static constexpr int kNibGroup = 4 * 2048, kTrGroup = 384;          // 4 x 80 B trailers, padded to the TMA alignment
     static constexpr int kXOff = 0;
-    static constexpr int kNibOff = kXOff + AS * kXStage;
-    static constexpr int kTrOff = kNibOff + RS * kNibStage;
-    static constexpr int kBarOff = kTrOff + RS * kTrStage;
-    static constexpr int kNumBars = 2 * RS + 3 * AS + 4;
+    static constexpr int kNibOff = kXOff + AS * KG * kXGroup;
+    static constexpr int kTrOff = kNibOff + RS * KG * kNibGroup;
+    static constexpr int kBarOff = kTrOff + RS * KG * kTrGroup;
+    static constexpr int kNumBars = 2 * RS + 2 * AS + 4;
     static constexpr int kMiscOff = kBarOff + kNumBars * 8;
     static constexpr int kBytes = kMiscOff + 16 + 1024;                 // + slack for the manual 1024-byte alignment
-    static_assert(kACol0 + AS * 64 <= 512, "TMEM columns");
+    static_assert(kACol0 + AS * KG * 64 <= 512, "TMEM columns");
     static_assert(kBytes <= 232448, "shared memory");
 };
 
@@ -224,17 +229,17 @@ struct TcSched {
     }
 };
 
-template <int NTOK, int NG>
-__global__ void __launch_bounds__(TsCfg<NTOK, NG>::kThreads, 1) k_w4a16_ts(const __grid_constant__ W4TcParams p) {
-    using C = TsCfg<NTOK, NG>;
+template <int NTOK>
+__global__ void __launch_bounds__(TsCfg<NTOK>::kThreads, 1) k_w4a16_ts(const __grid_constant__ W4TcParams p) {
+    using C = TsCfg<NTOK>;
+    constexpr int KG = C::KG, NG = C::NG;
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBarOff);
     uint64_t* raw_full = bars;
     uint64_t* raw_empty = raw_full + C::RS;
-    uint64_t* a_full = raw_empty + C::RS;
-    uint64_t* x_full = a_full + C::AS;
-    uint64_t* ax_empty = x_full + C::AS;
+    uint64_t* a_full = raw_empty + C::RS;      // dequant warps of the stage's group + the x producer (carries the x bytes)
+    uint64_t* ax_empty = a_full + C::AS;
     uint64_t* acc_full = ax_empty + C::AS;
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + C::kMiscOff);
@@ -245,7 +250,7 @@ __global__ void __launch_bounds__(TsCfg<NTOK, NG>::kThreads, 1) k_w4a16_ts(const
     const TcSched sch(n_tiles, G, (int)gridDim.x, (int)blockIdx.x);
     const bool tracing = (p.dbg & 16) && blockIdx.x == 0 && p.trace;
     auto stamp = [&](int role, int stage, int ev) {
-        if (tracing && stage < 64) p.trace[(role * 64 + stage) * 4 + ev] = clock64();
+        if (tracing && stage < 64) p.trace[(role * 64 + stage) * 8 + ev] = clock64();
     };
 
     if (threadIdx.x == 0) {
@@ -254,8 +259,7 @@ __global__ void __launch_bounds__(TsCfg<NTOK, NG>::kThreads, 1) k_w4a16_ts(const
             mbar_init(&raw_empty[i], C::GW);
         }
         for (int i = 0; i < C::AS; ++i) {
-            mbar_init(&a_full[i], C::GW + 1);   // dequant warps + the x producer (whose arrival carries the tile's bytes)
-            mbar_init(&x_full[i], 1);
+            mbar_init(&a_full[i], C::GW + 1);
             mbar_init(&ax_empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -282,17 +286,23 @@ __global__ void __launch_bounds__(TsCfg<NTOK, NG>::kThreads, 1) k_w4a16_ts(const
         for (int si = 0; si < sch.n_segs; ++si) {
             int tile, g0, g1;
             sch.seg(si, tile, g0, g1);
-            for (int gi = g0; gi < g1; ++gi, ++st_i) {
-                if (lane == 0) stamp(0, st_i, 0);
+            for (int gi = g0; gi < g1; gi += KG, ++st_i) {
+                const int ng = min(KG, g1 - gi);
                 mbar_wait_wd(&raw_empty[rs], ph ^ 1u, p.err, 0x100 + rs);
                 if (lane == 0) stamp(0, st_i, 1);
                 if (tc_elect_one()) {
                     if (p.dbg & 8) {
                         mbar_arrive(&raw_full[rs]);
                     } else {
-                        mbar_expect_tx(&raw_full[rs], C::kNibStage + 4 * 80);
-                        tma_load_4d_hint(smem + C::kNibOff + rs * C::kNibStage, &p.wmap, 0, 0, gi, tile * 4, &raw_full[rs], pol);
-                        tma_load_3d_hint(smem + C::kTrOff + rs * C::kTrStage, &p.tmap, 0, gi, tile * 4, &raw_full[rs], pol);
+                        mbar_expect_tx(&raw_full[rs], (uint32_t)ng * (C::kNibGroup + 4 * 80));
+#pragma unroll
+                        for (int j = 0; j < KG; ++j)
+                            if (j < ng) {
+                                tma_load_4d_hint(smem + C::kNibOff + (rs * KG + j) * C::kNibGroup, &p.wmap, 0, 0, gi + j, tile * 4,
+                                                 &raw_full[rs], pol);
+                                tma_load_3d_hint(smem + C::kTrOff + (rs * KG + j) * C::kTrGroup, &p.tmap, 0, gi + j, tile * 4,
+                                                 &raw_full[rs], pol);
+                            }
                     }
                 }
                 __syncwarp();
@@ -310,17 +320,22 @@ __global__ void __launch_bounds__(TsCfg<NTOK, NG>::kThreads, 1) k_w4a16_ts(const
         for (int si = 0; si < sch.n_segs; ++si) {
             int tile, g0, g1;
             sch.seg(si, tile, g0, g1);
-            for (int gi = g0; gi < g1; ++gi, ++st_i) {
+            for (int gi = g0; gi < g1; gi += KG, ++st_i) {
+                const int ng = min(KG, g1 - gi);
                 mbar_wait_wd(&ax_empty[as], ph ^ 1u, p.err, 0x200 + as);
                 if (lane == 0) stamp(1, st_i, 1);
                 if (tc_elect_one()) {
                     if (p.dbg & 1) {
                         mbar_arrive(&a_full[as]);
                     } else {
-                        mbar_expect_tx(&a_full[as], C::kXStage);
-                        uint8_t* dst = smem + C::kXOff + as * C::kXStage;
-                        tma_load_2d(dst, &p.xmap, gi * kW4GroupK, 0, &a_full[as]);
-                        tma_load_2d(dst + NTOK * 128, &p.xmap, gi * kW4GroupK + 64, 0, &a_full[as]);
+                        mbar_expect_tx(&a_full[as], (uint32_t)ng * C::kXGroup);
+#pragma unroll
+                        for (int j = 0; j < KG; ++j)
+                            if (j < ng) {
+                                uint8_t* dst = smem + C::kXOff + (as * KG + j) * C::kXGroup;
+                                tma_load_2d(dst, &p.xmap, (gi + j) * kW4GroupK, 0, &a_full[as]);
+                                tma_load_2d(dst + NTOK * 128, &p.xmap, (gi + j) * kW4GroupK + 64, 0, &a_full[as]);
+                            }
                     }
                 }
                 __syncwarp();
@@ -341,25 +356,28 @@ __global__ void __launch_bounds__(TsCfg<NTOK, NG>::kThreads, 1) k_w4a16_ts(const
             mbar_wait_wd(&acc_empty[acc], acc_ph ^ 1u, p.err, 0x300 + acc);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NTOK);
-            for (int gi = g0; gi < g1; ++gi, ++st_i) {
+            for (int gi = g0; gi < g1; gi += KG, ++st_i) {
+                const int ng = min(KG, g1 - gi);
                 if (lane == 0) stamp(2, st_i, 0);
-                mbar_wait_wd(&a_full[as], ph, p.err, 0x400 + as);   // 8 dequant arrivals + the x tile's bytes
-                if (lane == 0) stamp(2, st_i, 2);
+                mbar_wait_wd(&a_full[as], ph, p.err, 0x400 + as);   // dequant arrivals + the x tiles' bytes
+                if (lane == 0) stamp(2, st_i, 1);
                 tc_fence_after();
-                const uint32_t a_col = tmem_base + (uint32_t)(C::kACol0 + as * 64);
-                const uint64_t xd0 = tc_desc_sw128(smem_u32(smem + C::kXOff + as * C::kXStage));
                 if (tc_elect_one()) {
-                    if (!(p.dbg & 4) || gi == g0) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)   // 16 k = 8 TMEM columns of A; x: 64-k atom j / 4, 32 bytes per step inside it
-                            tc_mma_f16_ts(d_tmem, a_col + (uint32_t)(j * 8),
-                                          xd0 + (uint64_t)((j >> 2) * ((NTOK * 128) >> 4) + (j & 3) * 2), idesc,
-                                          (gi > g0 || j > 0) ? 1u : 0u);
+                    for (int j = 0; j < KG; ++j) {
+                        if (j < ng && (!(p.dbg & 4) || gi + j == g0)) {
+                            const uint32_t a_col = tmem_base + (uint32_t)(C::kACol0 + (as * KG + j) * 64);
+                            const uint64_t xd0 = tc_desc_sw128(smem_u32(smem + C::kXOff + (as * KG + j) * C::kXGroup));
+#pragma unroll
+                            for (int jj = 0; jj < 8; ++jj)   // 16 k = 8 TMEM columns of A; x: 64-k atom jj / 4, 32 bytes per step
+                                tc_mma_f16_ts(d_tmem, a_col + (uint32_t)(jj * 8),
+                                              xd0 + (uint64_t)((jj >> 2) * ((NTOK * 128) >> 4) + (jj & 3) * 2), idesc,
+                                              (gi + j > g0 || jj > 0) ? 1u : 0u);
+                        }
                     }
-                    tc_commit(&ax_empty[as]);   // frees the A columns and the x stage once the MMAs above have read them
-                    if (gi + 1 == g1) tc_commit(&acc_full[acc]);
+                    tc_commit(&ax_empty[as]);   // frees the A columns and the x tiles once the MMAs above have read them
+                    if (gi + KG >= g1) tc_commit(&acc_full[acc]);
                 }
-                __syncwarp();
                 if (lane == 0) stamp(2, st_i, 3);
                 if (++as == C::AS) {
                     as = 0;
@@ -372,24 +390,25 @@ __global__ void __launch_bounds__(TsCfg<NTOK, NG>::kThreads, 1) k_w4a16_ts(const
             }
         }
     } else if (warp >= C::kWarpDq0) {
-        // ---------------- dequant: the lane owns packed row 32 q + lane of the tile, k-slice ks; group grp takes every NG-th
-        // stage, so that while one group sits in its barrier / TMEM-store round trip the others are converting ----------------
+        // ---------------- dequant: the lane owns packed row 32 q + lane of the tile, k-slice ks of each group; the two warp
+        // groups take the stages alternately, so that while one sits in its barrier / TMEM-store round trip the other converts
         const int dw = warp - C::kWarpDq0;
         const int grp = dw / C::GW, q = warp & 3, ks = (dw % C::GW) >> 2;
         const int tt = lane >> 4, hi = (lane >> 3) & 1, g = lane & 7;
-        constexpr int KW = kW4GroupK / C::KQ;            // k per warp and stage: 64 (KQ = 2)
-        constexpr int NCH = KW / 16;                     // 16-k chunks (one uint4 each) per lane and stage
+        constexpr int KW = kW4GroupK / C::KQ;            // k per warp and group: 64
+        constexpr int NCH = KW / 16;                     // 16-k chunks (one uint4 each) per lane and group
         const uint32_t mask = hi ? 0xf0f0f0f0u : 0x0f0f0f0fu;
         const uint32_t magic = hi ? 0x54545454u : 0x64646464u;   // 64 + n / 16 for a high nibble n, 1024 + n for a low one
         const uint32_t sw = (uint32_t)(g >> 1) & 3u;     // the map's 64-byte swizzle: chunk ^= (row >> 1) & 3, row % 8 = g
         const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(C::kACol0 + ks * (KW / 2));
-        const int trole = 3 + (dw & 7);                  // trace roles 3..10: the eight warps of group 0
+        const int trole = 3 + (dw % C::GW);              // trace roles 3..10: the warps of group 0
         int st_i = 0;
         for (int si = 0; si < sch.n_segs; ++si) {
             int tile, g0, g1;
             sch.seg(si, tile, g0, g1);
-            for (int gi = g0; gi < g1; ++gi, ++st_i) {
+            for (int gi = g0; gi < g1; gi += KG, ++st_i) {
                 if (st_i % NG != grp) continue;
+                const int ng = min(KG, g1 - gi);
                 const int rs = st_i % C::RS, as = st_i % C::AS;
                 const uint32_t rph = (uint32_t)(st_i / C::RS) & 1u, aph = (uint32_t)(st_i / C::AS) & 1u;
                 if (lane == 0) {
@@ -398,45 +417,54 @@ __global__ void __launch_bounds__(TsCfg<NTOK, NG>::kThreads, 1) k_w4a16_ts(const
                     if (grp == 0) stamp(trole, st_i, 1);
                 }
                 __syncwarp();
-                const uint8_t* nib = smem + C::kNibOff + rs * C::kNibStage + q * 2048;
-                const uint8_t* tr = smem + C::kTrOff + rs * C::kTrStage + q * 80;
-                uint4 wv[NCH];
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    // 16-k chunk kc of the group: k = 32 t + 16 hh + ..., record row (2 tt + hh) * 8 + g, chunk t
-                    const int kc = ks * NCH + c, t = kc >> 1, hh = kc & 1;
-                    wv[c] = *reinterpret_cast<const uint4*>(nib + ((tt * 2 + hh) * 8 + g) * 64 + (((uint32_t)t ^ sw) << 4));
-                }
-                const __half2 sc2 = *reinterpret_cast<const __half2*>(tr + (tt * 8 + g) * 4);
-                const int zz = tr[64 + tt * 8 + g];
-                __syncwarp();                       // every lane's shared-memory reads of the stage have returned
-                if (lane == 0) mbar_arrive(&raw_empty[rs]);
-                const __half2 cz = __float2half2_rn(hi ? (float)(64 + (zz >> 4)) : (float)(1024 + (zz & 0xF)));
-                const __half2 s2 = hi ? __half2half2(__high2half(sc2)) : __half2half2(__low2half(sc2));
-                if (lane == 0) {
-                    mbar_wait_wd(&ax_empty[as], aph ^ 1u, p.err, 0x700 + as);
-                    if (grp == 0) stamp(trole, st_i, 2);
-                }
-                __syncwarp();
-                tc_fence_after();
-                if (!(p.dbg & 2)) {
+                for (int j = 0; j < KG; ++j) {
+                    if (j < ng) {
+                        const uint8_t* nib = smem + C::kNibOff + (rs * KG + j) * C::kNibGroup + q * 2048;
+                        const uint8_t* tr = smem + C::kTrOff + (rs * KG + j) * C::kTrGroup + q * 80;
+                        uint4 wv[NCH];
 #pragma unroll
-                    for (int c2 = 0; c2 < NCH; c2 += 2) {   // 32 k = 16 columns per tcgen05.st
-                        uint32_t r[16];
+                        for (int c = 0; c < NCH; ++c) {
+                            // 16-k chunk kc of the group: k = 32 t + 16 hh + ..., record row (2 tt + hh) * 8 + g, chunk t
+                            const int kc = ks * NCH + c, t = kc >> 1, hh = kc & 1;
+                            wv[c] = *reinterpret_cast<const uint4*>(nib + ((tt * 2 + hh) * 8 + g) * 64 + (((uint32_t)t ^ sw) << 4));
+                        }
+                        const __half2 sc2 = *reinterpret_cast<const __half2*>(tr + (tt * 8 + g) * 4);
+                        const int zz = tr[64 + tt * 8 + g];
+                        if (j == ng - 1) {
+                            __syncwarp();               // every lane's shared-memory reads of the stage have returned
+                            if (lane == 0) mbar_arrive(&raw_empty[rs]);
+                        }
+                        const __half2 cz = __float2half2_rn(hi ? (float)(64 + (zz >> 4)) : (float)(1024 + (zz & 0xF)));
+                        const __half2 s2 = hi ? __half2half2(__high2half(sc2)) : __half2half2(__low2half(sc2));
+                        if (j == 0) {
+                            if (lane == 0) {
+                                mbar_wait_wd(&ax_empty[as], aph ^ 1u, p.err, 0x700 + as);
+                                if (grp == 0) stamp(trole, st_i, 2);
+                            }
+                            __syncwarp();
+                            tc_fence_after();
+                        }
+                        if (!(p.dbg & 2)) {
 #pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            const uint32_t words[4] = {wv[c2 + c].x, wv[c2 + c].y, wv[c2 + c].z, wv[c2 + c].w};
+                            for (int c2 = 0; c2 < NCH; c2 += 2) {   // 32 k = 16 columns per tcgen05.st
+                                uint32_t r[16];
 #pragma unroll
-                            for (int wq = 0; wq < 4; ++wq) {
-                                const uint32_t wm = words[wq] & mask;
-                                uint32_t a0 = __byte_perm(wm, magic, 0x4140), a1 = __byte_perm(wm, magic, 0x4342);
-                                __half2 v0 = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&a0), cz), s2);
-                                __half2 v1 = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&a1), cz), s2);
-                                r[c * 8 + wq * 2] = *reinterpret_cast<uint32_t*>(&v0);
-                                r[c * 8 + wq * 2 + 1] = *reinterpret_cast<uint32_t*>(&v1);
+                                for (int c = 0; c < 2; ++c) {
+                                    const uint32_t words[4] = {wv[c2 + c].x, wv[c2 + c].y, wv[c2 + c].z, wv[c2 + c].w};
+#pragma unroll
+                                    for (int wq = 0; wq < 4; ++wq) {
+                                        const uint32_t wm = words[wq] & mask;
+                                        uint32_t a0 = __byte_perm(wm, magic, 0x4140), a1 = __byte_perm(wm, magic, 0x4342);
+                                        __half2 v0 = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&a0), cz), s2);
+                                        __half2 v1 = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&a1), cz), s2);
+                                        r[c * 8 + wq * 2] = *reinterpret_cast<uint32_t*>(&v0);
+                                        r[c * 8 + wq * 2 + 1] = *reinterpret_cast<uint32_t*>(&v1);
+                                    }
+                                }
+                                tc_st16(lane_taddr + (uint32_t)((as * KG + j) * 64 + c2 * 8), r);
                             }
                         }
-                        tc_st16(lane_taddr + (uint32_t)(as * 64 + c2 * 8), r);
                     }
                 }
                 tc_wait_st();
@@ -558,12 +586,11 @@ cudaError_t prepare_w4_tc() {
         st->err = st->counters + kTcMaxTiles;
         st->ws_bytes = kTcWsBytes;
     }
-#define ZL_TS_SET(NT, NG)                                                                                         \
-    if ((e = cudaFuncSetAttribute(k_w4a16_ts<NT, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,                 \
-                                  TsCfg<NT, NG>::kBytes)) != cudaSuccess)                                          \
+#define ZL_TS_SET(NT)                                                                                             \
+    if ((e = cudaFuncSetAttribute(k_w4a16_ts<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
+                                  TsCfg<NT>::kBytes)) != cudaSuccess)                                              \
         return e;
-    ZL_TS_SET(32, 1) ZL_TS_SET(64, 1) ZL_TS_SET(128, 1) ZL_TS_SET(256, 1)
-    ZL_TS_SET(32, 2) ZL_TS_SET(64, 2) ZL_TS_SET(128, 2) ZL_TS_SET(256, 2)
+    ZL_TS_SET(32) ZL_TS_SET(64) ZL_TS_SET(128) ZL_TS_SET(256)
 #undef ZL_TS_SET
     return cudaSuccess;
 }
@@ -695,24 +722,12 @@ cudaError_t launch_w4_tc(const W4Params& p, bool pdl, cudaStream_t stream) {
     const int ctas = tc_pick_ctas(n_tiles, G);
     if ((size_t)2 * ctas * p.mc * kTcRows * 4 > st->ws_bytes - (1 << 20)) return cudaErrorInvalidValue;
     const dim3 grid(ctas);
-    static const int ng = getenv("ZL_TC_GROUPS") ? atoi(getenv("ZL_TC_GROUPS")) : 2;   // dequant groups (A/B: 1)
-#define ZL_TS_LAUNCH(NT, NG) \
-    return launch(k_w4a16_ts<NT, NG>, grid, dim3(TsCfg<NT, NG>::kThreads), (size_t)TsCfg<NT, NG>::kBytes, stream, pdl, q)
-    if (ng == 1) {
-        switch (ntok) {
-            case 32: ZL_TS_LAUNCH(32, 1);
-            case 64: ZL_TS_LAUNCH(64, 1);
-            case 128: ZL_TS_LAUNCH(128, 1);
-            default: ZL_TS_LAUNCH(256, 1);
-        }
-    }
     switch (ntok) {
-        case 32: ZL_TS_LAUNCH(32, 2);
-        case 64: ZL_TS_LAUNCH(64, 2);
-        case 128: ZL_TS_LAUNCH(128, 2);
-        default: ZL_TS_LAUNCH(256, 2);
+        case 32: return launch(k_w4a16_ts<32>, grid, dim3(TsCfg<32>::kThreads), (size_t)TsCfg<32>::kBytes, stream, pdl, q);
+        case 64: return launch(k_w4a16_ts<64>, grid, dim3(TsCfg<64>::kThreads), (size_t)TsCfg<64>::kBytes, stream, pdl, q);
+        case 128: return launch(k_w4a16_ts<128>, grid, dim3(TsCfg<128>::kThreads), (size_t)TsCfg<128>::kBytes, stream, pdl, q);
+        default: return launch(k_w4a16_ts<256>, grid, dim3(TsCfg<256>::kThreads), (size_t)TsCfg<256>::kBytes, stream, pdl, q);
     }
-#undef ZL_TS_LAUNCH
 }
 
 }  // namespace zl
