@@ -116,10 +116,14 @@ int zl_w4a16_gemm(const void* x, int ldx, const void* packed, const void* bias, 
  *   tp_mode (tensor parallel, integer kernel only; replaces ModelContext::reduce_sum + element_add_scale between a
  *                       row-parallel Linear and the next column-parallel one, model_context.cpp:203-243, block.cpp:123-141):
  *                       2 on the row-parallel GEMM (o_proj / w_out, epilogue NONE, y unused): the fp16 partial tile is
- *                       stored straight into every rank's NVLink-mapped inbox of tp_comm and the epoch flags are published;
+ *                       stored straight into every rank's NVLink-mapped inbox of tp_comm as 8-byte words {2 x fp16, tag}
+ *                       (valid on arrival: no flags, no fences);
  *                       1 on the next GEMM: its activation row becomes T(T(sum_r partial_r) + x), x = residual stream,
- *                       reduced in rank order while the activations are staged; the sum is also stored to tp_h_out
- *                       (M, K; must not alias x).  0: off.
+ *                       reduced in rank order while the activations are staged (the staging loop polls the words' tags);
+ *                       the sum is also stored to tp_h_out (M, K; must not alias x).  0: off.
+ *                       tp_index: index of the exchange within the step (< 512, the same on producer and consumer, consecutive
+ *                       exchanges alternate parity); zl_comm_ll_begin_step(tp_comm) must be enqueued once per step before
+ *                       the first such GEMM, on every rank.
  * bias is indexed by PACKED row. */
 typedef struct zl_comm zl_comm_t;
 typedef struct zl_w4_fused_args {
@@ -131,7 +135,7 @@ typedef struct zl_w4_fused_args {
     int num_heads, num_kv_heads, dim_head;
     const void* prefetch_ptr; size_t prefetch_bytes; /* next kernel's weights: pulled into L2 as this one drains (may be NULL) */
     int variant; /* layout of `packed`: 0 ZLW4, 1 ZLW4I (integer kernel; needs the staged activations to fit smem) */
-    zl_comm_t* tp_comm; int tp_mode; void* tp_h_out;
+    zl_comm_t* tp_comm; int tp_mode; void* tp_h_out; int tp_index;
 } zl_w4_fused_args_t;
 int zl_w4a16_gemm_fused(const zl_w4_fused_args_t* args, zl_stream_t stream);
 /* 1 if the exact-integer kernel (variant 1, M <= 16) can run this shape: its staged activations must fit shared memory. */
@@ -300,6 +304,9 @@ int zl_comm_world_size(zl_comm_t* c);
 int zl_comm_ipc_handle_bytes(void);
 int zl_comm_get_ipc_handle(zl_comm_t* c, void* handle_out);
 int zl_comm_open_peers(zl_comm_t* c, const void* handles_all);
+/* once per decode step that uses the exchange fused into the W4 GEMMs (tp_mode of zl_w4a16_gemm_fused), before the first
+ * such GEMM of the step and on every rank: advances the step counter the word tags are derived from. */
+int zl_comm_ll_begin_step(zl_comm_t* c, zl_stream_t stream);
 /* out = T(T(sum over ranks of partial) + residual); n % 32 == 0; residual may be NULL; out may alias residual.
  * int8_payload != 0: peers' contributions travel as int8 + one T scale per 32 values (the reference's group-32
  * format, int8/quant_reduce_kernel.cu:14-38); deterministic rank-ordered fp32 reduction either way. */

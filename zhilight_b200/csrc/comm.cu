@@ -228,6 +228,7 @@ struct zl_comm {
     CommDev* dev = nullptr;
     unsigned long long* epoch = nullptr;
     unsigned int* done = nullptr;
+    unsigned int* ll_step = nullptr;
     bool opened = false;
 };
 
@@ -246,6 +247,8 @@ extern "C" int zl_comm_create(int rank, int world_size, size_t max_elems_16bit, 
     ZL_CHECK_CUDA(cudaMalloc((void**)&c->done, 4));
     ZL_CHECK_CUDA(cudaMemset(c->epoch, 0, 8));
     ZL_CHECK_CUDA(cudaMemset(c->done, 0, 4));
+    ZL_CHECK_CUDA(cudaMalloc((void**)&c->ll_step, 4));
+    ZL_CHECK_CUDA(cudaMemset(c->ll_step, 0, 4));
     c->peers[rank] = c->local;
     if (world_size == 1) {
         CommDev h = {};
@@ -255,6 +258,7 @@ extern "C" int zl_comm_create(int rank, int world_size, size_t max_elems_16bit, 
         h.slot_bytes = c->slot_bytes;
         h.epoch = c->epoch;
         h.done = c->done;
+        h.ll_step = c->ll_step;
         ZL_CHECK_CUDA(cudaMemcpy(c->dev, &h, sizeof(h), cudaMemcpyHostToDevice));
         c->opened = true;
     }
@@ -291,6 +295,7 @@ extern "C" int zl_comm_open_peers(zl_comm_t* c, const void* handles_all) {
     h.slot_bytes = c->slot_bytes;
     h.epoch = c->epoch;
     h.done = c->done;
+    h.ll_step = c->ll_step;
     ZL_CHECK_CUDA(cudaMemcpy(c->dev, &h, sizeof(h), cudaMemcpyHostToDevice));
     c->opened = true;
     return ZL_OK;
@@ -305,12 +310,26 @@ extern "C" void zl_comm_destroy(zl_comm_t* c) {
     cudaFree(c->dev);
     cudaFree(c->epoch);
     cudaFree(c->done);
+    cudaFree(c->ll_step);
     delete c;
 }
 
 extern "C" int zl_comm_rank(zl_comm_t* c) { return c ? c->rank : -1; }
 extern "C" const void* zl_comm_device_state(zl_comm_t* c) { return (c && c->opened) ? c->dev : nullptr; }
 extern "C" size_t zl_comm_slot_bytes(zl_comm_t* c) { return c ? c->slot_bytes : 0; }
+
+__global__ void k_comm_ll_step(unsigned int* step) {
+    pdl_trigger();
+    pdl_wait();
+    if (threadIdx.x == 0) *step += 1u;
+}
+// once per decode step that uses the tagged exchange, before its first GEMM: every rank runs the same steps, so the counters
+// (and with them the tags) agree without any communication
+extern "C" int zl_comm_ll_begin_step(zl_comm_t* c, zl_stream_t stream) {
+    ZL_CHECK_ARG(c && c->opened);
+    ZL_CHECK_CUDA(launch(k_comm_ll_step, dim3(1), dim3(32), 0, stream, false, c->ll_step));
+    return ZL_OK;
+}
 extern "C" int zl_comm_world_size(zl_comm_t* c) { return c ? c->ws : -1; }
 
 extern "C" int zl_allreduce_one_shot(zl_comm_t* c, const void* partial, const void* residual, void* out, size_t n,

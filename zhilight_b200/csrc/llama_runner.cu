@@ -675,7 +675,7 @@ static int no_pdl_mask() {
 
 int w4_gemm(zl_llama* m, const void* x, int ldx, const W4Lin& w, const void* residual, void* y, int B, int epi,
             const void* ln_w, const Layer* rope_layer, int layer = -1, int slot = -1, int row0 = 0, int force_no_pdl = 0,
-            int tp_mode = 0, void* tp_h_out = nullptr) {
+            int tp_mode = 0, void* tp_h_out = nullptr, int tp_index = 0) {
     const auto& c = m->cfg;
     zl_w4_fused_args_t a = {};
     a.x = x;
@@ -734,6 +734,7 @@ int w4_gemm(zl_llama* m, const void* x, int ldx, const W4Lin& w, const void* res
         a.tp_comm = m->comm;
         a.tp_mode = tp_mode;
         a.tp_h_out = tp_h_out;
+        a.tp_index = tp_index;
     }
     return zl_w4a16_gemm_fused(&a, m->stream);
 }
@@ -897,15 +898,17 @@ int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* p
     // other of the two buffers h / h2.  Only the last layer's w_out keeps the stand-alone one-shot kernel (the final norm
     // is not a GEMM).  ZL_TP_UNFUSED=1 keeps the separate exchange kernels everywhere (A/B).
     bool tp_fused = tp && w4 && !pf && c.fuse >= 1 && !c.tp_int8 && dt == ZL_F16 && !getenv("ZL_TP_UNFUSED") && !skip &&
-                    (size_t)B * D * 2 <= zl_comm_slot_bytes(m->comm);
+                    (size_t)B * D * 2 <= zl_comm_slot_bytes(m->comm) && 2 * c.num_layers <= 512;
     if (tp_fused) {
         const Layer& L0 = m->layers[0];
         for (const W4Lin* w : {&L0.q_qkv, &L0.q_o, &L0.q_gu, &L0.q_down})
             if (!w->packed_i || zl_w4_int_layout_route(B, w->N, w->K) != 3) tp_fused = false;
     }
+    if (tp_fused) RCHECK(zl_comm_ll_begin_step(m->comm, st));   // the word tags of this step's exchanges
     void* hc = m->h;    // current residual stream
     void* ho = m->h2;   // where the next fused reduce-in writes it
     bool pending = false;   // partial sums of the previous row-parallel GEMM are in flight to the inboxes
+    int xi = 0;             // index of the next exchange of the step (producer and consumer use the same one)
     for (int l = 0; l < (dual ? 0 : c.num_layers); ++l) {
         Layer& L = m->layers[l];
         if (w4) {
@@ -920,9 +923,9 @@ int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* p
             const int tpm = pending ? 1 : 0;
             if (skip & 2) {
             } else if (c.fuse >= 2) {
-                RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, nullptr, B, ZL_EPI_QKV_ROPE, lnw, &L, l, 0, 0, 0, tpm, ho));
+                RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, nullptr, B, ZL_EPI_QKV_ROPE, lnw, &L, l, 0, 0, 0, tpm, ho, xi - 1));
             } else {
-                RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, m->qkv, B, ZL_EPI_NONE, lnw, nullptr, l, 0, 0, 0, tpm, ho));
+                RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, m->qkv, B, ZL_EPI_NONE, lnw, nullptr, l, 0, 0, 0, tpm, ho, xi - 1));
             }
             if (pending) {
                 std::swap(hc, ho);
@@ -954,7 +957,7 @@ int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* p
         if (w4) {
             if (skip & 4) {
             } else if (tp_fused) {
-                RCHECK(w4_gemm(m, m->ao, m->hq * d, L.q_o, nullptr, nullptr, B, ZL_EPI_NONE, nullptr, nullptr, l, 2, 0, 0, 2));
+                RCHECK(w4_gemm(m, m->ao, m->hq * d, L.q_o, nullptr, nullptr, B, ZL_EPI_NONE, nullptr, nullptr, l, 2, 0, 0, 2, nullptr, xi++));
                 pending = true;
             } else if (tp) {
                 // row-parallel: partial sums -> one-shot NVLink all-reduce fused with the residual add
@@ -972,14 +975,14 @@ int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* p
                 RCHECK(zl_rmsnorm(hc, L.ln_ff, m->xn, B, D, c.eps, 1.f, dt, pdl, st));
             }
             if (!(skip & 8))
-                RCHECK(w4_gemm(m, xin, D, L.q_gu, nullptr, m->act, B, ZL_EPI_SWIGLU, lnw, nullptr, l, 3, 0, 0, pending ? 1 : 0, ho));
+                RCHECK(w4_gemm(m, xin, D, L.q_gu, nullptr, m->act, B, ZL_EPI_SWIGLU, lnw, nullptr, l, 3, 0, 0, pending ? 1 : 0, ho, xi - 1));
             if (pending) {
                 std::swap(hc, ho);
                 pending = false;
             }
             if (skip & 16) {
             } else if (tp_fused && l + 1 < c.num_layers) {
-                RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, nullptr, nullptr, B, ZL_EPI_NONE, nullptr, nullptr, l, 4, 0, 0, 2));
+                RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, nullptr, nullptr, B, ZL_EPI_NONE, nullptr, nullptr, l, 4, 0, 0, 2, nullptr, xi++));
                 pending = true;
             } else if (tp) {
                 RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, nullptr, m->pend, B, ZL_EPI_NONE, nullptr, nullptr, l, 4));

@@ -37,6 +37,7 @@ struct W4Params {
     // fp16 partial tile into every rank's inbox and the last CTA publishes the epoch flags.
     const void* tp_cd = nullptr;   // const CommDev*
     int tp_mode = 0;
+    int tp_index = 0;              // exchange index within the step (< 512): parity of the slot + part of the word tag
     __half* tp_h_out = nullptr;
 };
 

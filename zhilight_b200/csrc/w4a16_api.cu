@@ -117,6 +117,7 @@ extern "C" int zl_w4a16_gemm_fused(const zl_w4_fused_args_t* a, zl_stream_t stre
     const void* tp_cd = nullptr;
     if (a->tp_mode != 0) {
         ZL_CHECK_ARG(a->tp_mode == 1 || a->tp_mode == 2);
+        ZL_CHECK_ARG(a->tp_index >= 0 && a->tp_index < 512);
         ZL_CHECK_ARG(a->tp_comm != nullptr && a->variant == kW4VariantInt);
         tp_cd = zl_comm_device_state(a->tp_comm);
         if (!tp_cd) {
@@ -174,6 +175,7 @@ extern "C" int zl_w4a16_gemm_fused(const zl_w4_fused_args_t* a, zl_stream_t stre
         if (p.dbg & 32) p.ln_w = nullptr;   // timing probe: drop the fused RMSNorm (results are wrong)
         p.tp_cd = tp_cd;
         p.tp_mode = a->tp_mode;
+        p.tp_index = a->tp_index;
         p.tp_h_out = static_cast<__half*>(a->tp_h_out);
         p.pf_ptr = static_cast<const uint8_t*>(a->prefetch_ptr);
         p.pf_bytes = a->prefetch_bytes;

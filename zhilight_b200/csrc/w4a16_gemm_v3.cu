@@ -147,12 +147,12 @@ __device__ __forceinline__ void pack_blocks(const W4Params& p, const uint8_t* ri
 // 16-bit activation mantissas share ONE IMMA: column 2i carries token i's high digit, column 2i+1 its low digit, both
 // signed (m = 256*hi' + lo', lo' = int8(m & 0xff), hi' = (m + 128) >> 8, |m| <= 2^14).  Half the IMMAs, half the B
 // loads, and the per-group int->float epilogue only touches real tokens.
-template <int NT, bool NORM, int WARPS, int SUBS, int STAGES, int RT = NT * 8, bool PACK = false, bool TPX = false>
+template <int NT, bool NORM, int WARPS, int SUBS, int STAGES, int RT = NT * 8, bool PACK = false, int TPX = 0>
 __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Params p) {
     using S = V3Smem<NT, WARPS, SUBS, STAGES, RT>;
     // the tensor-parallel exchange code is compiled only into the TPX instantiations: carried as a run-time branch it cost
     // every launch 10-20 registers (to the 128-register cap of the 512-thread CTA) and ~5 % of a single-GPU decode step
-    const int tp_mode = TPX ? p.tp_mode : 0;
+    constexpr int tp_mode = TPX;   // 0 none, 1 reduce-in while staging, 2 push from the epilogue (== p.tp_mode, checked by the launcher)
     constexpr int WT = WARPS * SUBS;
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -247,26 +247,21 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
     pdl_wait();   // everything above touched only constants; x / residual / KV come from predecessor kernels
     stamp();
 
-    // ---- tensor-parallel reduce-in: wait until every peer has pushed its partial sums of the previous row-parallel
-    // GEMM into this rank's inbox (flag[src][0] >= epoch; the local producer already advanced the epoch) ----
+    // ---- tensor-parallel reduce-in: the partial sums of the previous row-parallel GEMM arrive in this rank's inbox as
+    // 8-byte words {2 x fp16, tag}; a word is valid once its tag is the tag of this exchange (comm_dev.cuh) -- no flags,
+    // no fences: the staging loop below polls the words it needs ----
     const CommDev* tp = static_cast<const CommDev*>(p.tp_cd);
-    const uint8_t* tp_slots = nullptr;   // [ws][slot_bytes] of the exchange's parity
-    size_t tp_slot_bytes = 0;
+    const uint8_t* tp_slots = nullptr;   // [ws][2 * slot_bytes] of the exchange's parity
+    size_t tp_slot_bytes = 0;            // bytes of one source's tagged slot
     int tp_ws = 0;
-    if (tp_mode == 1) {
-        const unsigned long long ep = *reinterpret_cast<volatile unsigned long long*>(tp->epoch);
+    uint32_t tp_tag = 0;
+    if (tp_mode != 0) {
         tp_ws = tp->ws;
-        tp_slot_bytes = tp->slot_bytes;
-        const uint8_t* mine = tp->inbox[tp->rank];
-        if ((int)threadIdx.x < tp_ws && (int)threadIdx.x != tp->rank) {
-            const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(mine + comm_flags_offset(tp_ws, tp_slot_bytes)) +
-                                             (size_t)threadIdx.x * kCommMaxCtas;
-            while (ld_acquire_sys(flag) < ep) {
-            }
-        }
-        tp_slots = mine + ((ep - 1ull) & 1ull) * (size_t)tp_ws * tp_slot_bytes;
-        __syncthreads();
+        tp_slot_bytes = 2 * tp->slot_bytes;
+        tp_tag = comm_ll_tag(*reinterpret_cast<volatile unsigned int*>(tp->ll_step), p.tp_index);
     }
+    if (tp_mode == 1)
+        tp_slots = tp->inbox[tp->rank] + comm_ll_offset(tp_ws, tp->slot_bytes) + (size_t)(p.tp_index & 1) * tp_ws * tp_slot_bytes;
 
     // ---- stage the activations as block-floating-point integers, once per CTA ----
     for (int tok = 0; tok < p.mc; ++tok) {
@@ -278,38 +273,34 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
         }
         if (tp_mode == 1) {
             // x := T(T(sum_r partial_r) + x): fp32 sum in rank order (identical on every rank and CTA), the reference's
-            // reduce_sum + element_add_scale rounding points (model_context.cpp:203-243, block_kernel.cu:7-17)
-            float acc[kMaxNg][4];
-#pragma unroll
-            for (int gl = 0; gl < kMaxNg; ++gl) acc[gl][0] = acc[gl][1] = acc[gl][2] = acc[gl][3] = 0.f;
-            for (int r = 0; r < tp_ws; ++r) {
-                const __half* src = reinterpret_cast<const __half*>(tp_slots + (size_t)r * tp_slot_bytes) + (size_t)tok * p.K;
-                uint2 t[kMaxNg];
-#pragma unroll
-                for (int gl = 0; gl < kMaxNg; ++gl) {
-                    const int gi = warp + gl * WT;
-                    if (gi < G) t[gl] = ld_cg_u2(src + gi * kW4GroupK + lane * 4);
-                }
-#pragma unroll
-                for (int gl = 0; gl < kMaxNg; ++gl) {
-                    const int gi = warp + gl * WT;
-                    if (gi < G) {
-                        const float2 a = __half22float2(*reinterpret_cast<__half2*>(&t[gl].x));
-                        const float2 b = __half22float2(*reinterpret_cast<__half2*>(&t[gl].y));
-                        acc[gl][0] += a.x;
-                        acc[gl][1] += a.y;
-                        acc[gl][2] += b.x;
-                        acc[gl][3] += b.y;
-                    }
-                }
-            }
+            // reduce_sum + element_add_scale rounding points (model_context.cpp:203-243, block_kernel.cu:7-17).  One group
+            // at a time: the accumulators of all groups at once cost the 512-thread CTA its register budget.
+            // element i of token tok lives in word (tok * K + i) / 2 of the source's slot; this lane needs 4 elements = 2 words
+            const uint8_t* src0 = tp_slots + ((size_t)tok * p.K + lane * 4) * 4;
 #pragma unroll
             for (int gl = 0; gl < kMaxNg; ++gl) {
                 const int gi = warp + gl * WT;
                 if (gi < G) {
-                    const __half2 s01 = __floats2half2_rn(acc[gl][0], acc[gl][1]), s23 = __floats2half2_rn(acc[gl][2], acc[gl][3]);
-                    const __half2 h01 = __hadd2(s01, *reinterpret_cast<__half2*>(&raw[gl].x));
-                    const __half2 h23 = __hadd2(s23, *reinterpret_cast<__half2*>(&raw[gl].y));
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                    for (int r = 0; r < tp_ws; ++r) {
+                        const uint8_t* src = src0 + (size_t)r * tp_slot_bytes + (size_t)gi * kW4GroupK * 4;
+                        uint4 t = ld_ll2(src);
+                        if (t.y != tp_tag || t.w != tp_tag) {   // not there yet: poll (bounded: a lost peer must not hang the GPU)
+                            const long long t0 = clock64();
+                            do {
+                                t = ld_ll2(src);
+                                if (clock64() - t0 > 4000000000ll) __trap();
+                            } while (t.y != tp_tag || t.w != tp_tag);
+                        }
+                        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+                        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&t.z));
+                        a0 += a.x;
+                        a1 += a.y;
+                        a2 += b.x;
+                        a3 += b.y;
+                    }
+                    const __half2 h01 = __hadd2(__floats2half2_rn(a0, a1), *reinterpret_cast<__half2*>(&raw[gl].x));
+                    const __half2 h23 = __hadd2(__floats2half2_rn(a2, a3), *reinterpret_cast<__half2*>(&raw[gl].y));
                     raw[gl].x = *reinterpret_cast<const uint32_t*>(&h01);
                     raw[gl].y = *reinterpret_cast<const uint32_t*>(&h23);
                     if (blockIdx.x == 0)
@@ -386,15 +377,10 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
     __syncthreads();
     stamp();
 
-    // tensor-parallel push: slot (parity of the epoch, this rank) of every rank's inbox
-    int tp_push_ws = 0;
-    unsigned long long tp_epoch = 0;
+    // tensor-parallel push: tagged slot (parity of the exchange index, this rank) of every rank's inbox
     size_t tp_my_slot = 0;
-    if (tp_mode == 2) {
-        tp_epoch = *reinterpret_cast<volatile unsigned long long*>(tp->epoch);
-        tp_push_ws = tp->ws;
-        tp_my_slot = ((size_t)(tp_epoch & 1ull) * tp->ws + tp->rank) * tp->slot_bytes;
-    }
+    if (tp_mode == 2)
+        tp_my_slot = comm_ll_offset(tp_ws, tp->slot_bytes) + ((size_t)(p.tp_index & 1) * tp_ws + tp->rank) * tp_slot_bytes;
 
     int c_slot = 0;
     uint32_t c_parity = 0;
@@ -632,45 +618,43 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
                 }
             }
         } else {
-            for (int e = stid; e < p.mc * 32; e += kSubThreads) {
-                const int tok = e >> 5, row = e & 31;
-                float v = sum_red(tok * 32 + row);
-                if (NORM) v *= s_rstd[tok];
-                v += s_poison[tok];
-                if (p.bias) v += __half2float(p.bias[n0 + row]);
-                __half h = __float2half_rn(v);
-                if (tp_mode == 2) {   // partial sum of a row-parallel GEMM: straight into every rank's inbox (own slot too)
-                    for (int r = 0; r < tp_push_ws; ++r)
-                        reinterpret_cast<__half*>(tp->inbox[r] + tp_my_slot)[(size_t)tok * p.N + n0 + row] = h;
-                    continue;
+            if (tp_mode == 2) {
+                // partial sums of a row-parallel GEMM: pairs of rows as one tagged 8-byte word straight into every rank's
+                // inbox (own slot too); the word's tag makes it valid on arrival, nothing else is published
+                for (int e = stid; e < p.mc * 16; e += kSubThreads) {
+                    const int tok = e >> 4, row = (e & 15) * 2;
+                    float v0 = sum_red(tok * 32 + row), v1 = sum_red(tok * 32 + row + 1);
+                    if (NORM) {
+                        v0 *= s_rstd[tok];
+                        v1 *= s_rstd[tok];
+                    }
+                    v0 += s_poison[tok];
+                    v1 += s_poison[tok];
+                    if (p.bias) {
+                        v0 += __half2float(p.bias[n0 + row]);
+                        v1 += __half2float(p.bias[n0 + row + 1]);
+                    }
+                    const __half2 h2 = __floats2half2_rn(v0, v1);
+                    const size_t word = ((size_t)tok * p.N + n0 + row) >> 1;
+                    for (int r = 0; r < tp_ws; ++r)
+                        st_ll(tp->inbox[r] + tp_my_slot + word * 8, *reinterpret_cast<const uint32_t*>(&h2), tp_tag);
                 }
-                if (p.epi == ZL_EPI_RESIDUAL)
-                    h = __float2half_rn(__half2float(h) + __half2float(p.residual[(size_t)tok * p.N + n0 + row]));
-                p.y[(size_t)tok * p.N + n0 + row] = h;
+            } else {
+                for (int e = stid; e < p.mc * 32; e += kSubThreads) {
+                    const int tok = e >> 5, row = e & 31;
+                    float v = sum_red(tok * 32 + row);
+                    if (NORM) v *= s_rstd[tok];
+                    v += s_poison[tok];
+                    if (p.bias) v += __half2float(p.bias[n0 + row]);
+                    __half h = __float2half_rn(v);
+                    if (p.epi == ZL_EPI_RESIDUAL)
+                        h = __float2half_rn(__half2float(h) + __half2float(p.residual[(size_t)tok * p.N + n0 + row]));
+                    p.y[(size_t)tok * p.N + n0 + row] = h;
+                }
             }
         }
         if (S::kRedBufs == 1) sub_barrier(1 + sub, WARPS * 32);
         stamp();
-    }
-    if (tp_mode == 2) {
-        // every store of this CTA is fenced to system scope, then the last CTA of the grid publishes the flags: the peers'
-        // next GEMM (reduce-in above) acquires them.  Advancing the local epoch tells the local consumer which exchange
-        // to wait for.
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            if (atomicAdd(tp->done, 1u) == gridDim.x - 1) {
-                *tp->done = 0;
-                __threadfence_system();
-                for (int r = 0; r < tp_push_ws; ++r)
-                    if (r != tp->rank)
-                        st_release_sys(reinterpret_cast<unsigned long long*>(tp->inbox[r] + comm_flags_offset(tp->ws, tp->slot_bytes)) +
-                                           (size_t)tp->rank * kCommMaxCtas,
-                                       tp_epoch + 1);
-                __threadfence();
-                *reinterpret_cast<volatile unsigned long long*>(tp->epoch) = tp_epoch + 1;
-            }
-        }
     }
 }
 
@@ -686,7 +670,10 @@ static cudaError_t launch_v3_t(const W4Params& p, int smem, bool pdl, cudaStream
     if (p.tp_mode != 0) {
         // exchange variants exist for the 4-stage rings only (launch_w4_v3 routes tensor-parallel launches there)
         if constexpr (STAGES == 4 && RT == NT * 8) {
-            return launch(k_w4a16_v3<NT, NORM, WARPS, SUBS, STAGES, RT, PACK, true>, dim3(grid), dim3(WARPS * SUBS * 32),
+            if (p.tp_mode == 1)
+                return launch(k_w4a16_v3<NT, NORM, WARPS, SUBS, STAGES, RT, PACK, 1>, dim3(grid), dim3(WARPS * SUBS * 32),
+                              (size_t)smem, stream, pdl, p);
+            return launch(k_w4a16_v3<NT, NORM, WARPS, SUBS, STAGES, RT, PACK, 2>, dim3(grid), dim3(WARPS * SUBS * 32),
                           (size_t)smem, stream, pdl, p);
         } else {
             return cudaErrorNotSupported;
@@ -804,7 +791,10 @@ cudaError_t prepare_w4_v3() {
     ZL_SET(2, false, 8, 2, 4) ZL_SET(2, true, 8, 2, 4) ZL_SET(2, false, 16, 1, 4) ZL_SET(2, true, 16, 1, 4)
 #undef ZL_SET
 #define ZL_SETX(NT, NORM, W, SB, PK)                                                                            \
-    e = cudaFuncSetAttribute(k_w4a16_v3<NT, NORM, W, SB, 4, NT * 8, PK, true>,                                  \
+    e = cudaFuncSetAttribute(k_w4a16_v3<NT, NORM, W, SB, 4, NT * 8, PK, 1>,                                     \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, kV3Budget);                           \
+    if (e != cudaSuccess) return e;                                                                             \
+    e = cudaFuncSetAttribute(k_w4a16_v3<NT, NORM, W, SB, 4, NT * 8, PK, 2>,                                     \
                              cudaFuncAttributeMaxDynamicSharedMemorySize, kV3Budget);                           \
     if (e != cudaSuccess) return e;
     ZL_SETX(1, false, 8, 2, false) ZL_SETX(1, true, 8, 2, false) ZL_SETX(1, false, 16, 1, false) ZL_SETX(1, true, 16, 1, false)
