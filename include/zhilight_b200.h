@@ -121,9 +121,10 @@ int zl_w4a16_gemm(const void* x, int ldx, const void* packed, const void* bias, 
  *                       1 on the next GEMM: its activation row becomes T(T(sum_r partial_r) + x), x = residual stream,
  *                       reduced in rank order while the activations are staged (the staging loop polls the words' tags);
  *                       the sum is also stored to tp_h_out (M, K; must not alias x).  0: off.
- *                       tp_index: index of the exchange within the step (< 512, the same on producer and consumer, consecutive
- *                       exchanges alternate parity); zl_comm_ll_begin_step(tp_comm) must be enqueued once per step before
- *                       the first such GEMM, on every rank.
+ *                       tp_index: index of the exchange within the step (0 .. 511, consecutive, the same on producer and
+ *                       consumer), | 512 when the step has an ODD number of exchanges (the two slots must alternate across
+ *                       step boundaries too); zl_comm_ll_begin_step(tp_comm) must be enqueued once per step before the
+ *                       first such GEMM, on every rank.
  * bias is indexed by PACKED row. */
 typedef struct zl_comm zl_comm_t;
 typedef struct zl_w4_fused_args {

@@ -123,3 +123,55 @@ def test_gloo_world_size_2_bootstrap_and_protocol():
     assert sorted(r[0] for r in res) == [0, 1]
     for r in res:
         assert r[1] and r[2] and r[3], r
+
+
+def _ll_tag(step, index):
+    """comm_ll_tag of zhilight_b200/csrc/comm_dev.cuh: 32-bit, never 0."""
+    return ((step << 9) + index + 1) & 0xFFFFFFFF
+
+
+@pytest.mark.parametrize("X", [4, 5])
+@pytest.mark.parametrize("ws", [2, 4])
+def test_tagged_exchange_protocol_model(ws, X):
+    """Model of the exchange that rides inside the W4 GEMMs (w4a16_gemm_v3.cu tp_mode 1 / 2): every rank runs, per step,
+    PUSH(x) then CONSUME(x) for x = 0 .. X-1; a word is accepted iff its tag is the tag of (step, x); consecutive exchanges
+    alternate between two slots ACROSS step boundaries too (parity = (x + step * (X & 1)) & 1 -- with parity = x & 1 and an
+    odd X this model finds the overwrite of an unconsumed word at the step boundary).
+    Under every interleaving the dependencies allow (a rank may run ahead until it needs a word that has not arrived),
+    no rank may ever read a stale word as valid and no word may be overwritten before its receiver consumed it."""
+    rng = np.random.default_rng(ws)
+    steps = 4
+    for trial in range(200):
+        inbox = [[[(0, None)] * ws for _ in range(2)] for _ in range(ws)]      # [receiver][parity][source] = (tag, payload)
+        consumed = [[[True] * ws for _ in range(2)] for _ in range(ws)]       # was the current content read by its receiver?
+        pc = [0] * ws                                   # program counter: 2 * (step * X + x) + (0 push | 1 consume)
+        end = 2 * steps * X
+        gidx = [0] * ws                                 # exchanges pushed so far, over all steps (parity = gidx of that exchange & 1)
+        while any(p < end for p in pc):
+            ready = []
+            for r in range(ws):
+                if pc[r] >= end:
+                    continue
+                step, x = divmod(pc[r] // 2, X)
+                if pc[r] % 2 == 0:
+                    ready.append(r)                     # a push never blocks
+                else:
+                    par = (x + step * (X & 1)) & 1
+                    if all(inbox[r][par][s][0] == _ll_tag(step + 1, x) for s in range(ws)):
+                        ready.append(r)
+            assert ready, "deadlock"
+            r = int(rng.choice(ready))
+            step, x = divmod(pc[r] // 2, X)
+            par = (x + step * (X & 1)) & 1
+            if pc[r] % 2 == 0:
+                for dst in range(ws):
+                    assert consumed[dst][par][r], "overwrote a word its receiver had not consumed"
+                    inbox[dst][par][r] = (_ll_tag(step + 1, x), (r, step, x))
+                    consumed[dst][par][r] = False
+                gidx[r] += 1
+            else:
+                for s in range(ws):
+                    tag, payload = inbox[r][par][s]
+                    assert payload == (s, step, x), "accepted a stale word"
+                    consumed[r][par][s] = True
+            pc[r] += 1

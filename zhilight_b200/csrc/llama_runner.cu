@@ -909,6 +909,7 @@ int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* p
     void* ho = m->h2;   // where the next fused reduce-in writes it
     bool pending = false;   // partial sums of the previous row-parallel GEMM are in flight to the inboxes
     int xi = 0;             // index of the next exchange of the step (producer and consumer use the same one)
+    const int xodd = ((2 * c.num_layers - 1) & 1) << 9;   // 2 L - 1 exchanges per step: odd -> bit 9 of tp_index
     for (int l = 0; l < (dual ? 0 : c.num_layers); ++l) {
         Layer& L = m->layers[l];
         if (w4) {
@@ -923,9 +924,9 @@ int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* p
             const int tpm = pending ? 1 : 0;
             if (skip & 2) {
             } else if (c.fuse >= 2) {
-                RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, nullptr, B, ZL_EPI_QKV_ROPE, lnw, &L, l, 0, 0, 0, tpm, ho, xi - 1));
+                RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, nullptr, B, ZL_EPI_QKV_ROPE, lnw, &L, l, 0, 0, 0, tpm, ho, (xi - 1) | xodd));
             } else {
-                RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, m->qkv, B, ZL_EPI_NONE, lnw, nullptr, l, 0, 0, 0, tpm, ho, xi - 1));
+                RCHECK(w4_gemm(m, xin, D, L.q_qkv, nullptr, m->qkv, B, ZL_EPI_NONE, lnw, nullptr, l, 0, 0, 0, tpm, ho, (xi - 1) | xodd));
             }
             if (pending) {
                 std::swap(hc, ho);
@@ -957,7 +958,7 @@ int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* p
         if (w4) {
             if (skip & 4) {
             } else if (tp_fused) {
-                RCHECK(w4_gemm(m, m->ao, m->hq * d, L.q_o, nullptr, nullptr, B, ZL_EPI_NONE, nullptr, nullptr, l, 2, 0, 0, 2, nullptr, xi++));
+                RCHECK(w4_gemm(m, m->ao, m->hq * d, L.q_o, nullptr, nullptr, B, ZL_EPI_NONE, nullptr, nullptr, l, 2, 0, 0, 2, nullptr, (xi++) | xodd));
                 pending = true;
             } else if (tp) {
                 // row-parallel: partial sums -> one-shot NVLink all-reduce fused with the residual add
@@ -975,14 +976,14 @@ int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* p
                 RCHECK(zl_rmsnorm(hc, L.ln_ff, m->xn, B, D, c.eps, 1.f, dt, pdl, st));
             }
             if (!(skip & 8))
-                RCHECK(w4_gemm(m, xin, D, L.q_gu, nullptr, m->act, B, ZL_EPI_SWIGLU, lnw, nullptr, l, 3, 0, 0, pending ? 1 : 0, ho, xi - 1));
+                RCHECK(w4_gemm(m, xin, D, L.q_gu, nullptr, m->act, B, ZL_EPI_SWIGLU, lnw, nullptr, l, 3, 0, 0, pending ? 1 : 0, ho, (xi - 1) | xodd));
             if (pending) {
                 std::swap(hc, ho);
                 pending = false;
             }
             if (skip & 16) {
             } else if (tp_fused && l + 1 < c.num_layers) {
-                RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, nullptr, nullptr, B, ZL_EPI_NONE, nullptr, nullptr, l, 4, 0, 0, 2, nullptr, xi++));
+                RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, nullptr, nullptr, B, ZL_EPI_NONE, nullptr, nullptr, l, 4, 0, 0, 2, nullptr, (xi++) | xodd));
                 pending = true;
             } else if (tp) {
                 RCHECK(w4_gemm(m, m->act, m->ff, L.q_down, nullptr, m->pend, B, ZL_EPI_NONE, nullptr, nullptr, l, 4));

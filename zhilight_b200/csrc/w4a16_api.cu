@@ -117,7 +117,7 @@ extern "C" int zl_w4a16_gemm_fused(const zl_w4_fused_args_t* a, zl_stream_t stre
     const void* tp_cd = nullptr;
     if (a->tp_mode != 0) {
         ZL_CHECK_ARG(a->tp_mode == 1 || a->tp_mode == 2);
-        ZL_CHECK_ARG(a->tp_index >= 0 && a->tp_index < 512);
+        ZL_CHECK_ARG(a->tp_index >= 0 && a->tp_index < 1024);
         ZL_CHECK_ARG(a->tp_comm != nullptr && a->variant == kW4VariantInt);
         tp_cd = zl_comm_device_state(a->tp_comm);
         if (!tp_cd) {

@@ -255,13 +255,19 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
     size_t tp_slot_bytes = 0;            // bytes of one source's tagged slot
     int tp_ws = 0;
     uint32_t tp_tag = 0;
+    int tp_parity = 0;
     if (tp_mode != 0) {
         tp_ws = tp->ws;
         tp_slot_bytes = 2 * tp->slot_bytes;
-        tp_tag = comm_ll_tag(*reinterpret_cast<volatile unsigned int*>(tp->ll_step), p.tp_index);
+        const unsigned int step = *reinterpret_cast<volatile unsigned int*>(tp->ll_step);
+        const int idx = p.tp_index & 511;
+        tp_tag = comm_ll_tag(step, idx);
+        // consecutive exchanges alternate between the two slots, across step boundaries too: bit 9 of tp_index says that the
+        // step has an odd number of exchanges (then the parity sequence flips every step; tests/test_dist_cpu.py models why)
+        tp_parity = (idx + ((p.tp_index >> 9) & 1) * (int)(step & 1u)) & 1;
     }
     if (tp_mode == 1)
-        tp_slots = tp->inbox[tp->rank] + comm_ll_offset(tp_ws, tp->slot_bytes) + (size_t)(p.tp_index & 1) * tp_ws * tp_slot_bytes;
+        tp_slots = tp->inbox[tp->rank] + comm_ll_offset(tp_ws, tp->slot_bytes) + (size_t)tp_parity * tp_ws * tp_slot_bytes;
 
     // ---- stage the activations as block-floating-point integers, once per CTA ----
     for (int tok = 0; tok < p.mc; ++tok) {
@@ -380,7 +386,7 @@ __global__ void __launch_bounds__(WARPS * SUBS * 32, 1) k_w4a16_v3(const W4Param
     // tensor-parallel push: tagged slot (parity of the exchange index, this rank) of every rank's inbox
     size_t tp_my_slot = 0;
     if (tp_mode == 2)
-        tp_my_slot = comm_ll_offset(tp_ws, tp->slot_bytes) + ((size_t)(p.tp_index & 1) * tp_ws + tp->rank) * tp_slot_bytes;
+        tp_my_slot = comm_ll_offset(tp_ws, tp->slot_bytes) + ((size_t)tp_parity * tp_ws + tp->rank) * tp_slot_bytes;
 
     int c_slot = 0;
     uint32_t c_parity = 0;
