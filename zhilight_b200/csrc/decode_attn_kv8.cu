@@ -154,61 +154,71 @@ k_decode_attn_kv8(const __half* __restrict__ q, const int32_t* __restrict__ buf_
     }
     __syncthreads();
 
-    // ---- phase 3: O = (P * scale_v) . (V - 128) in fp32 ----
-    const int dc = tid % DC, sub = tid / DC;
-    float o[8][8];
+    // ---- phase 3: O = (P * scale_v) . (V - 128) on the tensor cores (mma.sync m16n8k16, fp32 accumulate) ----
+    // A = weights [head (8 of 16 rows) x 16 keys] as fp16 (scaled by 2^10 so that small probabilities stay normal numbers),
+    // B = V [16 keys x 8 columns] as exact fp16 integers.  A B fragment register holds TWO KEYS of one column, V is stored
+    // key-major: lane (g, t) loads D/8 contiguous bytes (columns NJ g .. NJ g + NJ - 1) of its four keys 2t, 2t+1, 2t+8,
+    // 2t+9 and byte-interleaves row pairs with PRMT; n-tile j column c then stands for column d = NJ c + j of V (any
+    // permutation of the columns is as good as another -- it is undone when the accumulators are written out).
+    constexpr int NJ = D / 8;                        // n-tiles = V columns per lane and key row
+    constexpr int NW = NJ / 4;                       // 32-bit words of a lane's column chunk
+    float o[NJ][4];
 #pragma unroll
-    for (int h = 0; h < 8; ++h)
+    for (int j = 0; j < NJ; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+    const __half2 voff = __float2half2_rn(1152.f);   // 1024 (magic) + 128 (zero point of the cache)
+    for (int tile = warp; tile < ntiles; tile += kA8Warps) {
+        const int kb = tile * 16;                    // first key of the tile, relative to k0
+        uint32_t vw[4][NW];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[h][i] = 0.f;
-    const uint8_t* vp = vbase + (size_t)k0 * stride + dc * 8;
-    constexpr int U = 4;
-    for (int key = sub; key < n; key += NSUB * U) {
-        uint2 vv[U];
+        for (int r = 0; r < 4; ++r) {
+            const int kk = kb + 2 * t + (r & 1) + (r >> 1) * 8;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int kk = key + u * NSUB;
-            if (kk < n) vv[u] = ld_cg_b8(vp + (size_t)kk * stride);
+            for (int w = 0; w < NW; ++w) vw[r][w] = 0x80808080u;          // out of range: v - 128 = 0
+            if (kk < n) {
+                const uint8_t* src = vbase + (size_t)(k0 + kk) * stride + g * NJ;
+                if constexpr (NW == 4) {
+                    const uint4 v = ld_cg_u4(src);
+                    vw[r][0] = v.x, vw[r][1] = v.y, vw[r][2] = v.z, vw[r][3] = v.w;
+                } else {
+                    const uint2 v = ld_cg_b8(src);
+                    vw[r][0] = v.x, vw[r][1] = v.y;
+                }
+            }
+        }
+        uint32_t af[4] = {0u, 0u, 0u, 0u};
+        if (g < mq) {
+            const float* pr = s_logit + g * kA8RowStride + kb + 2 * t;
+            const float2 p0 = *reinterpret_cast<const float2*>(pr), p1 = *reinterpret_cast<const float2*>(pr + 8);
+            const bool in0 = kb + 2 * t < n, in1 = kb + 2 * t + 1 < n, in2 = kb + 2 * t + 8 < n, in3 = kb + 2 * t + 9 < n;
+            const __half2 h0 = __floats2half2_rn(in0 ? p0.x * 1024.f : 0.f, in1 ? p0.y * 1024.f : 0.f);
+            const __half2 h1 = __floats2half2_rn(in2 ? p1.x * 1024.f : 0.f, in3 ? p1.y * 1024.f : 0.f);
+            af[0] = *reinterpret_cast<const uint32_t*>(&h0);   // (head g, keys 2t, 2t+1)
+            af[2] = *reinterpret_cast<const uint32_t*>(&h1);   // (head g, keys 2t+8, 2t+9); rows g+8 (a1, a3) stay zero
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int kk = key + u * NSUB;
-            if (kk < n) {
-                float vf[8];
+        for (int wq = 0; wq < NW; ++wq) {
+            // bytes 4 wq .. 4 wq + 3 of the key pairs -> {k, k+1} interleaved
+            const uint32_t lo01 = __byte_perm(vw[0][wq], vw[1][wq], 0x5140), hi01 = __byte_perm(vw[0][wq], vw[1][wq], 0x7362);
+            const uint32_t lo23 = __byte_perm(vw[2][wq], vw[3][wq], 0x5140), hi23 = __byte_perm(vw[2][wq], vw[3][wq], 0x7362);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    vf[i] = u8_to_f32(vv[u].x, i);
-                    vf[4 + i] = u8_to_f32(vv[u].y, i);
-                }
-#pragma unroll
-                for (int h = 0; h < 8; ++h) {
-                    if (h < mq) {
-                        const float p = s_logit[h * kA8RowStride + kk];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) o[h][i] = fmaf(p, vf[i], o[h][i]);
-                    }
-                }
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t s01 = e < 2 ? lo01 : hi01, s23 = e < 2 ? lo23 : hi23;
+                const uint32_t sel = (e & 1) ? 0x4342u : 0x4140u;
+                uint32_t b0 = __byte_perm(s01, 0x64646464u, sel), b1 = __byte_perm(s23, 0x64646464u, sel);
+                __half2 hb0 = __hsub2(*reinterpret_cast<__half2*>(&b0), voff), hb1 = __hsub2(*reinterpret_cast<__half2*>(&b1), voff);
+                mma_16816_f16(o[wq * 4 + e], af, *reinterpret_cast<uint32_t*>(&hb0), *reinterpret_cast<uint32_t*>(&hb1), o[wq * 4 + e]);
             }
         }
     }
-#pragma unroll
-    for (int h = 0; h < 8; ++h)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float v = o[h][i];
-#pragma unroll
-            for (int off = DC; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-            o[h][i] = v;
-        }
     __syncthreads();
     float* s_red = s_logit;   // [warp][h][D]
-    if (lane < DC) {
+    if (g < mq) {
+        // accumulator (n-tile j, column c = 2t + i) = head g, V column NJ c + j; rows g + 8 (o[j][2..3]) are padding
 #pragma unroll
-        for (int h = 0; h < 8; ++h)
-            if (h < mq) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) s_red[(warp * 8 + h) * D + lane * 8 + i] = o[h][i];
-            }
+        for (int j = 0; j < NJ; ++j) {
+            s_red[(warp * 8 + g) * D + NJ * (2 * t) + j] = o[j][0] * (1.f / 1024.f);
+            s_red[(warp * 8 + g) * D + NJ * (2 * t + 1) + j] = o[j][1] * (1.f / 1024.f);
+        }
     }
     __syncthreads();
     for (int e = tid; e < mq * D; e += kA8Threads) {
