@@ -664,13 +664,16 @@ static void prefetch_target(zl_llama* m, int l, int slot, int B, const void** pt
 // 1 qkv GEMM, 2 attention, 4 o GEMM, 8 gate_up GEMM, 16 down GEMM, 32 final norm, 64 lm_head, 128 argmax.
 // Default 70 = lm_head + o GEMM + attention: a PDL-launched lm_head measured 128 us slower per step than a normally
 // launched one (tools/gpu_tail.sh); early-launched o GEMM / attention CTAs cost another ~1 % each.
-static int no_pdl_mask() {
-    static int v = -1;
-    if (v < 0) {
+static int no_pdl_mask(bool tensor_parallel = false) {
+    static int v = -2;
+    if (v == -2) {
         const char* e = getenv("ZL_NO_PDL_MASK");
-        v = e ? atoi(e) : 70;   // lm_head, o GEMM, attention: measured best (tools/gpu_pdlmask.sh: 640 -> 710 tok/s)
+        v = e ? atoi(e) : -1;
     }
-    return v;
+    if (v >= 0) return v;
+    // single GPU: lm_head, o GEMM, attention with full dependencies measured best (tools/gpu_pdlmask.sh: 640 -> 710 tok/s);
+    // tensor parallel (exchange inside the GEMMs): a PDL-launched attention kernel wins (N = 2: 783 vs 754 tok/s, r2s)
+    return tensor_parallel ? 68 : 70;
 }
 
 int w4_gemm(zl_llama* m, const void* x, int ldx, const W4Lin& w, const void* residual, void* y, int B, int epi,
@@ -712,7 +715,7 @@ int w4_gemm(zl_llama* m, const void* x, int ldx, const W4Lin& w, const void* res
     a.epilogue = epi;
     {
         const int bit = slot == 0 ? 1 : slot == 2 ? 4 : slot == 3 ? 8 : slot == 4 ? 16 : 0;
-        a.pdl = (no_pdl_mask() & bit) ? 0 : c.use_pdl;
+        a.pdl = (no_pdl_mask(c.tp_size > 1) & bit) ? 0 : c.use_pdl;
     }
     a.ln_weight = ln_w;
     a.eps = c.eps;
@@ -866,7 +869,7 @@ int enqueue_step(zl_llama* m, int n_tasks, int len_bucket, const PrefillChunk* p
     const int B = pf ? pf->n : n_tasks;   // rows (tokens) of every activation matrix in this launch sequence
     const int skip = debug_skip();
     const int D = c.dim_model, d = c.dim_head, dt = c.dtype, pdl = c.use_pdl;
-    const int npm = no_pdl_mask();
+    const int npm = no_pdl_mask(c.tp_size > 1);
     auto P = [&](int bit) { return (npm & bit) ? 0 : pdl; };
     cudaStream_t st = m->stream;
     const bool w4 = c.quant_type == 5 || c.quant_type == 6;
