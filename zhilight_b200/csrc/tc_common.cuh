@@ -59,6 +59,15 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16])
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+// tagged 8-byte words of the partial-tile exchange: {payload, tag}, one atomic store / load each
+__device__ __forceinline__ void tc_st_tag(uint2* p, uint32_t data, uint32_t tag) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(data), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint2 tc_ld_tag(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // true in exactly one lane of a converged warp (elect.sync): ptxas then knows the guarded region is single-threaded and passes
 // the tcgen05 operands through plain R2UR moves instead of a per-instruction ELECT / R2UR.BROADCAST waterfall loop
@@ -151,10 +160,13 @@ inline bool tc_make_map_nd(CUtensorMap* map, const void* base, CUtensorMapDataTy
 // per-device scratch of the split-k reductions: fp32 / int32 partial tiles, arrival counters, watchdog word
 struct TcDeviceState {
     float* ws = nullptr;
+    uint2* ws_ll = nullptr;            // W4 kernel: tagged partial-tile words {fp32 bits, tag}, all zero between launches
+    size_t ws_ll_bytes = 0;
     unsigned* counters = nullptr;
     unsigned* err = nullptr;
     size_t ws_bytes = 0;
 };
+constexpr size_t kTcWsLlBytes = 80ull << 20;   // >= 2 slots x 148 CTAs x 256 tokens x 128 rows x 8 B
 constexpr size_t kTcWsBytes = 64ull << 20;   // >= 2 x 148 items x 256 tokens x 128 rows x 4 B
 constexpr int kTcMaxTiles = 8192;
 TcDeviceState* tc_state();                   // w4a16_tc.cu; nullptr before prepare_w4_tc() ran on the current device

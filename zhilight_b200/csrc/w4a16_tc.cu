@@ -55,8 +55,8 @@ struct alignas(64) W4TcParams {
     __half* y;
     int M, N, K, epi;
     int dbg;                    // ZL_TC_DBG timing ablations (results are wrong): 1 no x loads, 2 no dequant, 4 no MMA, 8 no weight loads
-    float* ws;                  // [2 * CTA + slot][M][128] fp32 partial tiles
-    unsigned* counters;         // [tile] arrivals of the pieces of a shared tile, left at zero
+    uint2* ws;                  // [2 * CTA + slot][M][128] tagged words {fp32 partial sum, tag}: all zero between launches
+    float* ws_f32;              // plain scratch (its last MB carries the ZL_TC_DBG trace)
     unsigned* err;              // watchdog code
     long long* trace;           // ZL_TC_DBG & 16: clock64 stamps of CTA 0, [role][64 stages][8]
     const float* cos;
@@ -84,7 +84,12 @@ __device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, 
 // ---- epilogue of 16 tokens (c0 .. c0+15) for the weight row owned by this lane -----------------------------------------
 // Packed row p = tile * 128 + 32 * quadrant + lane.  Inside a 32-row block, rows (16 tt + g) and (16 tt + g + 8) are
 // partners (gate / up, RoPE low / high half): lane and lane + 8.
-__device__ __forceinline__ void tc_epilogue16(const W4TcParams& p, int prow, int lane, int c0, float (&v)[16]) {
+// the epilogue warps share their schedulers with the dequant warps, which are issue-bound: SiLU through the fast exp / divide
+// (2 ulp of fp32, invisible after the fp16 rounding of the product)
+__device__ __forceinline__ float tc_silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+__device__ __forceinline__ void tc_epilogue16(const W4TcParams& p, int prow, int lane, int c0, float (&v)[16],
+                                              const uint32_t* rpre = nullptr) {   // rpre: 16 residual halves, packed in pairs
     const float b = p.bias ? __half2float(p.bias[prow]) : 0.f;
     if (p.epi == ZL_EPI_SWIGLU) {
         const int n_out = p.N / 2;
@@ -94,7 +99,7 @@ __device__ __forceinline__ void tc_epilogue16(const W4TcParams& p, int prow, int
             const float mine = __half2float(__float2half_rn(v[i] + b));
             const float up = __shfl_down_sync(0xffffffffu, mine, 8);
             const int tok = c0 + i;
-            if (!(lane & 8) && tok < p.M) p.y[(size_t)tok * n_out + col] = __float2half_rn(silu_f(mine) * up);
+            if (!(lane & 8) && tok < p.M) p.y[(size_t)tok * n_out + col] = __float2half_rn(tc_silu(mine) * up);
         }
     } else if (p.epi == ZL_EPI_QKV_ROPE) {
         const int d = p.dim_head, half_dim = d / 2, tiles_per_head = d / 32;
@@ -139,8 +144,11 @@ __device__ __forceinline__ void tc_epilogue16(const W4TcParams& p, int prow, int
             const int tok = c0 + i;
             if (tok >= p.M) continue;
             __half h = __float2half_rn(v[i] + b);
-            if (p.epi == ZL_EPI_RESIDUAL)
-                h = __float2half_rn(__half2float(h) + __half2float(p.residual[(size_t)tok * p.N + prow]));
+            if (p.epi == ZL_EPI_RESIDUAL) {
+                const __half r = rpre ? __ushort_as_half((unsigned short)(rpre[i >> 1] >> ((i & 1) * 16)))
+                                      : p.residual[(size_t)tok * p.N + prow];
+                h = __float2half_rn(__half2float(h) + __half2float(r));
+            }
             p.y[(size_t)tok * p.N + prow] = h;
         }
     }
@@ -243,7 +251,6 @@ __global__ void __launch_bounds__(TsCfg<NTOK>::kThreads, 1) k_w4a16_ts(const __g
     uint64_t* acc_full = ax_empty + C::AS;
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + C::kMiscOff);
-    uint32_t* s_last = s_tmem + 1;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = p.K / kW4GroupK, n_tiles = p.N / kTcRows;
@@ -480,7 +487,6 @@ __global__ void __launch_bounds__(TsCfg<NTOK>::kThreads, 1) k_w4a16_ts(const __g
         // ---------------- epilogue: TMEM -> registers -> global ----------------
         const int q = warp;                      // TMEM lane quadrant this warp may read
         const int m = q * 32 + lane;             // row inside the tile
-        const int et = warp * 32 + lane;
         pdl_wait();
         int acc = 0;
         uint32_t acc_ph = 0;
@@ -493,16 +499,35 @@ __global__ void __launch_bounds__(TsCfg<NTOK>::kThreads, 1) k_w4a16_ts(const __g
             __syncwarp();
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NTOK);
-            float* wsp = whole ? nullptr : p.ws + ((size_t)sch.slot((int)blockIdx.x, tile) * p.M) * kTcRows + m;
+            uint2* wsp = whole ? nullptr : p.ws + ((size_t)sch.slot((int)blockIdx.x, tile) * p.M) * kTcRows + m;
+            // residual rows are one L2 round trip per 16-token chunk away: fetch the next chunk's while this one is processed
+            const bool pre = whole && p.epi == ZL_EPI_RESIDUAL;
+            uint32_t rnext[8];
+            auto fetch_res = [&](int c0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t lo = (c0 + 2 * i < p.M) ? __half_as_ushort(p.residual[(size_t)(c0 + 2 * i) * p.N + prow]) : 0u;
+                    const uint32_t hi = (c0 + 2 * i + 1 < p.M) ? __half_as_ushort(p.residual[(size_t)(c0 + 2 * i + 1) * p.N + prow]) : 0u;
+                    rnext[i] = lo | (hi << 16);
+                }
+            };
+            if (pre) fetch_res(0);
 #pragma unroll 1
             for (int c0 = 0; c0 < NTOK; c0 += 16) {
                 if (c0 >= p.M) break;
                 float v[16];
                 tc_ld16(taddr + (uint32_t)c0, v);
                 if (!whole) {
+                    // a piece of a shared tile: tagged words, valid on arrival (no fence, no counter)
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
-                        if (c0 + i < p.M) __stcg(wsp + (size_t)(c0 + i) * kTcRows, v[i]);
+                        if (c0 + i < p.M) tc_st_tag(wsp + (size_t)(c0 + i) * kTcRows, __float_as_uint(v[i]), 1u);
+                } else if (pre) {
+                    uint32_t rcur[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
+                    if (c0 + 16 < NTOK && c0 + 16 < p.M) fetch_res(c0 + 16);
+                    tc_epilogue16(p, prow, lane, c0, v, rcur);
                 } else {
                     tc_epilogue16(p, prow, lane, c0, v);
                 }
@@ -514,45 +539,56 @@ __global__ void __launch_bounds__(TsCfg<NTOK>::kThreads, 1) k_w4a16_ts(const __g
                 acc = 0;
                 acc_ph ^= 1u;
             }
-            if (!whole) {
-                // the last piece of the tile to arrive adds all pieces in k order and runs the epilogue
-                const int c_first = sch.owner((long long)tile * G), c_last = sch.owner((long long)(tile + 1) * G - 1);
-                const int nparts = c_last - c_first + 1;
-                __threadfence();
-                epi_bar();
-                if (et == 0) *s_last = (atomicAdd(&p.counters[tile], 1u) == (unsigned)(nparts - 1)) ? 1u : 0u;
-                epi_bar();
-                const bool last = *s_last != 0u;
-                epi_bar();   // s_last may be rewritten by the next piece
-                if (last) {
-                    __threadfence();
+        }
+        // ---- shared tiles: the owners of a tile's pieces split its 16-token chunks among themselves (chunk c goes to piece
+        // c mod nparts); each adds the pieces of its chunks in k order (deterministic), polling the tagged words, zeroes them for
+        // the next launch and runs the epilogue.  A CTA gets here only after it has written ALL its own pieces, so nobody ever
+        // waits for somebody who waits. ----
+        for (int si = 0; si < sch.n_segs && si < 2; ++si) {
+            int tile, g0, g1;
+            sch.seg(si, tile, g0, g1);
+            if (g0 == 0 && g1 == G) continue;
+            const int prow = tile * kTcRows + m;
+            const int c_first = sch.owner((long long)tile * G), c_last = sch.owner((long long)(tile + 1) * G - 1);
+            const int nparts = c_last - c_first + 1, part = (int)blockIdx.x - c_first;
 #pragma unroll 1
-                    for (int c0 = 0; c0 < p.M; c0 += 16) {
-                        float v[16];
+            for (int c0 = part * 16; c0 < p.M; c0 += nparts * 16) {
+                float v[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                for (int i = 0; i < 16; ++i) v[i] = 0.f;
 #pragma unroll 1
-                        for (int pp = 0; pp < nparts; pp += 2) {   // two pieces per L2 round trip
-                            const float* b0 = p.ws + ((size_t)sch.slot(c_first + pp, tile) * p.M) * kTcRows + m;
-                            const bool two = pp + 1 < nparts;
-                            const float* b1 = two ? p.ws + ((size_t)sch.slot(c_first + pp + 1, tile) * p.M) * kTcRows + m : b0;
-                            float t0[16], t1[16];
+                for (int pp = 0; pp < nparts; ++pp) {
+                    uint2* src = p.ws + ((size_t)sch.slot(c_first + pp, tile) * p.M + c0) * kTcRows + m;
+                    uint2 t[16];
+                    bool ok = true;
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const bool in = c0 + i < p.M;
-                                t0[i] = in ? __ldcg(b0 + (size_t)(c0 + i) * kTcRows) : 0.f;
-                                t1[i] = (in && two) ? __ldcg(b1 + (size_t)(c0 + i) * kTcRows) : 0.f;
-                            }
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                v[i] += t0[i];
-                                v[i] += t1[i];
-                            }
-                        }
-                        tc_epilogue16(p, prow, lane, c0, v);
+                    for (int i = 0; i < 16; ++i) {
+                        t[i] = (c0 + i < p.M) ? tc_ld_tag(src + (size_t)i * kTcRows) : make_uint2(0u, 1u);
+                        ok = ok && t[i].y == 1u;
                     }
-                    if (et == 0) p.counters[tile] = 0u;
+                    if (!ok) {                       // not all there yet: poll (bounded: a lost piece must not hang the GPU)
+                        const long long t_start = clock64();
+                        do {
+                            ok = true;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                if (t[i].y != 1u) t[i] = tc_ld_tag(src + (size_t)i * kTcRows);
+                                ok = ok && t[i].y == 1u;
+                            }
+                            if (clock64() - t_start > 4000000000ll) {
+                                if (p.err) atomicExch(p.err, 0x900u + (unsigned)pp);
+                                __threadfence_system();
+                                __trap();
+                            }
+                        } while (!ok);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        v[i] += __uint_as_float(t[i].x);
+                        if (c0 + i < p.M) tc_st_tag(src + (size_t)i * kTcRows, 0u, 0u);   // consumed: back to "empty"
+                    }
                 }
+                tc_epilogue16(p, prow, lane, c0, v);
             }
         }
     }
@@ -585,6 +621,9 @@ cudaError_t prepare_w4_tc() {
         if ((e = cudaMemset(st->counters, 0, (kTcMaxTiles + 16) * sizeof(unsigned))) != cudaSuccess) return e;
         st->err = st->counters + kTcMaxTiles;
         st->ws_bytes = kTcWsBytes;
+        if ((e = cudaMalloc((void**)&st->ws_ll, kTcWsLlBytes)) != cudaSuccess) return e;
+        if ((e = cudaMemset(st->ws_ll, 0, kTcWsLlBytes)) != cudaSuccess) return e;
+        st->ws_ll_bytes = kTcWsLlBytes;
     }
 #define ZL_TS_SET(NT)                                                                                             \
     if ((e = cudaFuncSetAttribute(k_w4a16_ts<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
@@ -705,8 +744,8 @@ cudaError_t launch_w4_tc(const W4Params& p, bool pdl, cudaStream_t stream) {
         static const int tc_dbg = getenv("ZL_TC_DBG") ? atoi(getenv("ZL_TC_DBG")) : 0;
         q.dbg = tc_dbg;
     }
-    q.ws = st->ws;
-    q.counters = st->counters;
+    q.ws = st->ws_ll;
+    q.ws_f32 = st->ws;
     q.err = st->err;
     q.trace = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(st->ws) + st->ws_bytes - (1 << 20));   // last MB of the workspace
     q.cos = p.cos;
@@ -720,7 +759,7 @@ cudaError_t launch_w4_tc(const W4Params& p, bool pdl, cudaStream_t stream) {
     q.num_kv_heads = p.num_kv_heads;
     q.dim_head = p.dim_head;
     const int ctas = tc_pick_ctas(n_tiles, G);
-    if ((size_t)2 * ctas * p.mc * kTcRows * 4 > st->ws_bytes - (1 << 20)) return cudaErrorInvalidValue;
+    if ((size_t)2 * ctas * p.mc * kTcRows * 8 > st->ws_ll_bytes) return cudaErrorInvalidValue;
     const dim3 grid(ctas);
     switch (ntok) {
         case 32: return launch(k_w4a16_ts<32>, grid, dim3(TsCfg<32>::kThreads), (size_t)TsCfg<32>::kBytes, stream, pdl, q);
