@@ -517,12 +517,12 @@ def main():
     out["roofline"] = {
         "bound": "hbm",
         "kernel": ("k_w8a8_skinny (+ activation quant)" if args.quant != "default" else "k_dense_skinny") if dense
-        else ("k_w4a16_v3 (integer IMMA, fused norm / RoPE / SwiGLU / residual variants as in the step)" if B <= 16
-              else "k_w4a16_tc (tcgen05 / TMEM / TMA)"),
+        else ("k_w4a16_v3 (integer IMMA, fused norm / RoPE / SwiGLU / residual variants as in the step)" if B <= 7
+              else "k_w4a16_ts (tcgen05, A operand in TMEM, tensor-TMA)"),
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
         "bytes_per_launch": g_bytes / g_launches, "us_per_launch": g_ms * 1e3 / iters / g_launches,
         "traffic": None,
-        "traffic_note": "dram bytes are not observable from inside the run; the ncu --set full capture of this kernel is in profiles/ (r02_*traffic*)",
+        "traffic_note": "dram bytes are not observable from inside the run; ncu --set full captures: profiles/r01_w4a16_traffic.json (integer kernel: dram reads = algorithmic bytes within 0.1 %), profiles/r02_w4a16_ts_ncu_full.txt (tcgen05 kernel: 61.4 MB read for 61.0 MB algorithmic)",
     }
 
     if extras:

@@ -1,4 +1,4 @@
-"""GPU parity: the tcgen05 / TMEM / TMA W4A16 kernel (k_w4a16_tc, ZLW4I layout) vs the CPU oracle.
+"""GPU parity: the tcgen05 W4A16 kernel (k_w4a16_ts: A operand in TMEM, ZLW4I layout) vs the CPU oracle.
 
 The kernel rounds w = (q - z) * s to fp16 once (what the reference's M > 40 dequant + cuBLASLt route does,
 q_gemm_k_major.cu:843-905, 1083-1100), multiplies fp16 x fp16 exactly and accumulates all of K in fp32 in TMEM.
