@@ -150,6 +150,10 @@ unsigned zl_w4_tc_watchdog(void);
 /* debug / tests: at least `splits` pieces per weight-row tile in the tcgen05 kernel's stream-k schedule (0 = automatic; also
  * ZL_TC_SPLITS). */
 int zl_w4_tc_set_splits(int splits);
+/* tests: host view of the tcgen05 kernel's stream-k schedule (the kernel's own scheduling code): pieces of CTA `cta` of `ctas`
+ * for n_tiles x G (tile, group) units; out[5 i ..] = tile, g0, g1, pieces of that tile, workspace slot (-1: whole tile);
+ * returns the number of pieces. */
+int zl_w4_tc_schedule(int n_tiles, int G, int ctas, int cta, int* out, int max_pieces);
 /* debug: with ZL_TC_DBG & 16, CTA 0 of the tcgen05 kernel stamps its pipeline hand-overs with clock64; copies
  * [11 roles][64 stages][4 events] of the last launch to `out` (n <= 2816 values). */
 int zl_w4_tc_read_trace(long long* out, int n);

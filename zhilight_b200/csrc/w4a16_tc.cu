@@ -191,7 +191,7 @@ struct TcSched {
     int G, P;
     long long U, u0, u1;
     int tile_a, a_g0, a_g1, tile_z, z_g1, n_segs;
-    __device__ TcSched(int n_tiles, int G_, int P_, int b) : G(G_), P(P_) {
+    __host__ __device__ TcSched(int n_tiles, int G_, int P_, int b) : G(G_), P(P_) {
         U = (long long)n_tiles * G;
         u0 = b * U / P;
         u1 = (b + 1) * U / P;
@@ -213,7 +213,7 @@ struct TcSched {
             n_segs = 2 + (tile_z - tile_a - 1);
         }
     }
-    __device__ void seg(int i, int& tile, int& g0, int& g1) const {
+    __host__ __device__ void seg(int i, int& tile, int& g0, int& g1) const {
         if (i == 0) {
             tile = tile_a;
             g0 = a_g0;
@@ -229,9 +229,9 @@ struct TcSched {
         }
     }
     // CTA that owns unit u
-    __device__ int owner(long long u) const { return (int)(((u + 1) * P + U - 1) / U) - 1; }
+    __host__ __device__ int owner(long long u) const { return (int)(((u + 1) * P + U - 1) / U) - 1; }
     // workspace slot of CTA c's piece of tile t: 2 c (+ 1 when the piece does not start the CTA's range)
-    __device__ int slot(int c, int t) const {
+    __host__ __device__ int slot(int c, int t) const {
         const long long cu0 = c * U / P, t0 = (long long)t * G;
         return 2 * c + ((cu0 >= t0) ? 0 : 1);
     }
@@ -655,6 +655,26 @@ extern "C" int zl_w4_tc_read_trace(long long* out, int n) {
                    cudaSuccess
                ? ZL_OK
                : ZL_ERR_CUDA;
+}
+
+// host view of the stream-k schedule of the tcgen05 kernel (the same TcSched the kernel uses), for tests: the pieces of CTA
+// `cta` out of `ctas` for n_tiles x G units.  out[5 * i + 0..4] = tile, g0, g1, number of pieces of that tile, workspace slot
+// of this piece (-1 for a whole tile); returns the number of pieces (<= max_pieces) or a negative error code.
+extern "C" int zl_w4_tc_schedule(int n_tiles, int G, int ctas, int cta, int* out, int max_pieces) {
+    if (n_tiles <= 0 || G <= 0 || ctas <= 0 || cta < 0 || cta >= ctas || !out || (long long)n_tiles * G < ctas) return ZL_ERR_INVALID_ARG;
+    const TcSched sch(n_tiles, G, ctas, cta);
+    if (sch.n_segs > max_pieces) return ZL_ERR_INVALID_ARG;
+    for (int i = 0; i < sch.n_segs; ++i) {
+        int tile, g0, g1;
+        sch.seg(i, tile, g0, g1);
+        const bool whole = g0 == 0 && g1 == G;
+        out[5 * i + 0] = tile;
+        out[5 * i + 1] = g0;
+        out[5 * i + 2] = g1;
+        out[5 * i + 3] = sch.owner((long long)(tile + 1) * G - 1) - sch.owner((long long)tile * G) + 1;
+        out[5 * i + 4] = whole ? -1 : sch.slot(cta, tile);
+    }
+    return sch.n_segs;
 }
 
 // grid override: ZL_TC_CTAS in the environment, or zl_w4_tc_set_splits(n) = "at least n pieces per tile" (tests exercise
